@@ -1,0 +1,257 @@
+// gcd_b200 — HBM-bound normalisation kernels on channels-last tensors.
+//   GroupNorm32 / Normalize : gcd-model/sgm/modules/diffusionmodules/util.py:259-276, attention.py:125-128,
+//                             model.py:52-55 (computed in fp32 like GroupNorm32.forward's x.float()).
+//   LayerNorm               : attention.py:456-572 (norm1-3), video_attention.py:15-143 (norm_in, norm1-3).
+// Roofline: pure streaming; stats pass reads the tensor once, apply pass reads once + writes act once.
+#include "common.cuh"
+#include "../../include/gcd_b200.h"
+#include <atomic>
+extern std::atomic<int64_t> g_launches;
+
+// ---------------------------------------------------------------------------------------------- GroupNorm stats
+// grid: (row_chunks, n_img). block: (C/4, RY). Each thread owns 4 consecutive channels = 2 channel pairs
+// (a pair never straddles a group because C/groups is even).
+template <bool IN_F32>
+__global__ void gn_stats_kernel(const void* __restrict__ in, int64_t rows, int C, int cpg, int rows_per_block,
+                                double* __restrict__ stats, int groups) {
+    __shared__ float s_sum[64], s_sq[64];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 64) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+    __syncthreads();
+    const int img = blockIdx.y;
+    const int c = threadIdx.x * 4;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const int64_t off = ((int64_t)img * rows + r) * C + c;
+        float x0, x1, x2, x3;
+        if (IN_F32) {
+            float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + off);
+            x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+        } else {
+            uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const act_t*>(in) + off);
+            float2 a = unpack2(v.x), b = unpack2(v.y);
+            x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y;
+        }
+        sa += x0 + x1; qa += x0 * x0 + x1 * x1;
+        sb += x2 + x3; qb += x2 * x2 + x3 * x3;
+    }
+    const int ga = c / cpg, gb = (c + 2) / cpg;
+    if (ga == gb) {
+        atomicAdd(&s_sum[ga], sa + sb);
+        atomicAdd(&s_sq[ga], qa + qb);
+    } else {
+        atomicAdd(&s_sum[ga], sa); atomicAdd(&s_sq[ga], qa);
+        atomicAdd(&s_sum[gb], sb); atomicAdd(&s_sq[gb], qb);
+    }
+    __syncthreads();
+    if (tid < groups) {
+        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 0], (double)s_sum[tid]);
+        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 1], (double)s_sq[tid]);
+    }
+}
+
+template <bool IN_F32>
+__global__ void gn_apply_kernel(const void* __restrict__ in, int64_t rows, int C, int cpg, int rows_per_block,
+                                const double* __restrict__ stats, int groups, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int do_silu, act_t* __restrict__ out) {
+    const int img = blockIdx.y;
+    const int c = threadIdx.x * 4;
+    const int ga = c / cpg, gb = (c + 2) / cpg;
+    const double cnt = (double)rows * (double)cpg;
+    float ma, ra, mb, rb;
+    {
+        double s = stats[((int64_t)img * groups + ga) * 2], q = stats[((int64_t)img * groups + ga) * 2 + 1];
+        double m = s / cnt, v = q / cnt - m * m;
+        ma = (float)m; ra = (float)(1.0 / sqrt((v > 0 ? v : 0) + (double)eps));
+        s = stats[((int64_t)img * groups + gb) * 2]; q = stats[((int64_t)img * groups + gb) * 2 + 1];
+        m = s / cnt; v = q / cnt - m * m;
+        mb = (float)m; rb = (float)(1.0 / sqrt((v > 0 ? v : 0) + (double)eps));
+    }
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const int64_t off = ((int64_t)img * rows + r) * C + c;
+        float x0, x1, x2, x3;
+        if (IN_F32) {
+            float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + off);
+            x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+        } else {
+            uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const act_t*>(in) + off);
+            float2 a = unpack2(v.x), bb = unpack2(v.y);
+            x0 = a.x; x1 = a.y; x2 = bb.x; x3 = bb.y;
+        }
+        x0 = (x0 - ma) * ra * g.x + b.x;
+        x1 = (x1 - ma) * ra * g.y + b.y;
+        x2 = (x2 - mb) * rb * g.z + b.z;
+        x3 = (x3 - mb) * rb * g.w + b.w;
+        if (do_silu) { x0 = ptx::silu(x0); x1 = ptx::silu(x1); x2 = ptx::silu(x2); x3 = ptx::silu(x3); }
+        *reinterpret_cast<uint2*>(out + off) = make_uint2(pack2(x0, x1), pack2(x2, x3));
+    }
+}
+
+static int gn_geometry(int64_t n_img, int64_t rows, int C, int groups, dim3* grid, dim3* block, int* rpb) {
+    GCD_REQUIRE(C % 4 == 0 && C / 4 <= 1024, "groupnorm: C=%d unsupported", C);
+    GCD_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0,
+                "groupnorm: C=%d groups=%d unsupported (need even channels per group, <=64 groups)", C, groups);
+    int bx = C / 4;
+    int by = 512 / bx;
+    if (by < 1) by = 1;
+    if (by > 64) by = 64;
+    // aim for >= ~4 blocks per SM overall, at least 2*by rows per block
+    int64_t want_blocks = 148 * 4;
+    int64_t chunks = want_blocks / (n_img > 0 ? n_img : 1);
+    if (chunks < 1) chunks = 1;
+    int64_t r = (rows + chunks - 1) / chunks;
+    int64_t minr = (int64_t)by * 4;
+    if (r < minr) r = minr;
+    *rpb = (int)r;
+    *grid = dim3((unsigned)((rows + r - 1) / r), (unsigned)n_img);
+    *block = dim3(bx, by);
+    GCD_REQUIRE(n_img <= 65535, "groupnorm: too many images (%lld)", (long long)n_img);
+    return 0;
+}
+
+extern "C" int gcd_groupnorm_stats(const void* in, int in_f32, int64_t n_img, int64_t rows, int C, int groups,
+                                   double* stats, void* stream) {
+    dim3 grid, block;
+    int rpb;
+    int rc = gn_geometry(n_img, rows, C, groups, &grid, &block, &rpb);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_f32)
+        gn_stats_kernel<true><<<grid, block, 0, st>>>(in, rows, C, C / groups, rpb, stats, groups);
+    else
+        gn_stats_kernel<false><<<grid, block, 0, st>>>(in, rows, C, C / groups, rpb, stats, groups);
+    GCD_CUDA_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+extern "C" int gcd_groupnorm_apply(const void* in, int in_f32, int64_t n_img, int64_t rows, int C, int groups,
+                                   const double* stats, const float* gamma, const float* beta, float eps, int silu,
+                                   void* out, void* stream) {
+    dim3 grid, block;
+    int rpb;
+    int rc = gn_geometry(n_img, rows, C, groups, &grid, &block, &rpb);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_f32)
+        gn_apply_kernel<true><<<grid, block, 0, st>>>(in, rows, C, C / groups, rpb, stats, groups, gamma, beta, eps, silu,
+                                                      (act_t*)out);
+    else
+        gn_apply_kernel<false><<<grid, block, 0, st>>>(in, rows, C, C / groups, rpb, stats, groups, gamma, beta, eps, silu,
+                                                       (act_t*)out);
+    GCD_CUDA_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; the row (<= 2048 channels) lives in registers: mean, then centred variance (two-pass, fp32).
+constexpr int LN_MAXK = 32;  // float2 per lane -> C <= 2048
+__global__ void layernorm_kernel(const float* __restrict__ in, int64_t rows, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, const float* __restrict__ add,
+                                 int64_t add_rows_per, int64_t add_mod, float* __restrict__ sum_out,
+                                 act_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int nk = C >> 6;  // float2 chunks per lane
+    const float2* src = reinterpret_cast<const float2*>(in + row * C);
+    const float2* ad = add ? reinterpret_cast<const float2*>(add + ((row / add_rows_per) % add_mod) * C) : nullptr;
+    float2 v[LN_MAXK];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXK; k++) {
+        if (k < nk) {
+            float2 t = src[lane + 32 * k];
+            if (ad) { float2 a = __ldg(&ad[lane + 32 * k]); t.x += a.x; t.y += a.y; }
+            v[k] = t;
+            s += t.x + t.y;
+        }
+    }
+    if (sum_out) {
+        float2* so = reinterpret_cast<float2*>(sum_out + row * C);
+#pragma unroll
+        for (int k = 0; k < LN_MAXK; k++)
+            if (k < nk) so[lane + 32 * k] = v[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXK; k++) {
+        if (k < nk) {
+            float dx = v[k].x - mean, dy = v[k].y - mean;
+            q += dx * dx + dy * dy;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    const float2* g2 = reinterpret_cast<const float2*>(gamma);
+    const float2* b2 = reinterpret_cast<const float2*>(beta);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + row * C);
+#pragma unroll
+    for (int k = 0; k < LN_MAXK; k++) {
+        if (k < nk) {
+            float2 g = __ldg(&g2[lane + 32 * k]), b = __ldg(&b2[lane + 32 * k]);
+            dst[lane + 32 * k] = pack2((v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y);
+        }
+    }
+}
+
+extern "C" int gcd_layernorm(const float* in, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                             const float* add, int64_t add_rows_per, int64_t add_mod, float* sum_out, void* out,
+                             void* stream) {
+    GCD_REQUIRE(C % 64 == 0 && C <= 64 * LN_MAXK, "layernorm: C=%d must be a multiple of 64 and <= %d", C, 64 * LN_MAXK);
+    GCD_REQUIRE(!add || (add_rows_per > 0 && add_mod > 0), "layernorm: bad add indexing");
+    const int warps = 8;
+    int64_t blocks = (rows + warps - 1) / warps;
+    layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(in, rows, C, gamma, beta, eps, add,
+                                                                                add_rows_per, add_mod, sum_out,
+                                                                                (act_t*)out);
+    GCD_CUDA_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- row softmax
+// model.py:161-201 AttnBlock: softmax(q k^T / sqrt(512)) with 9216 columns; one block per row, fp32 in, act out.
+__global__ void softmax_rows_kernel(const float* __restrict__ in, int cols, float scale, act_t* __restrict__ out) {
+    __shared__ float red[32];
+    const int64_t row = blockIdx.x;
+    const float* src = in + row * (int64_t)cols;
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) m = fmaxf(m, src[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < (blockDim.x >> 5); i++) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) s += __expf((src[j] - m) * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); i++) s += red[i];
+    const float inv = 1.0f / s;
+    act_t* dst = out + row * (int64_t)cols;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[j] = f2act(__expf((src[j] - m) * scale) * inv);
+}
+extern "C" int gcd_softmax_rows(const float* in, int64_t rows, int cols, float scale, void* out, void* stream) {
+    GCD_REQUIRE(rows < (1ll << 31), "softmax_rows: too many rows");
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(in, cols, scale, (act_t*)out);
+    GCD_CUDA_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}

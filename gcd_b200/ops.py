@@ -1,0 +1,221 @@
+"""Thin torch-tensor front end over the C ABI (include/gcd_b200.h). Tensors are only used for device memory and the
+current CUDA stream; every op launches hand-written sm_100a kernels from libgcd_b200.so. No fallbacks."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, TcOp, check
+
+
+def lib():
+    return _lib.load()
+
+
+_ACT = None
+
+
+def act_dtype():
+    """torch dtype of the 16-bit tensor-core operands the library was built for."""
+    global _ACT
+    if _ACT is None:
+        _ACT = torch.bfloat16 if lib().gcd_act_dtype() == 1 else torch.float16
+    return _ACT
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.GcdError("gcd_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def _is_f32(t):
+    if t.dtype == torch.float32:
+        return 1
+    if t.dtype == act_dtype():
+        return 0
+    raise _lib.GcdError(f"unsupported dtype {t.dtype} (expected float32 or {act_dtype()})")
+
+
+def _ld(t):
+    assert t.stride(-1) == 1, "last dim must be contiguous"
+    return t.stride(-2) if t.dim() >= 2 else t.numel()
+
+
+def make_ep(out, bias=None, rowvec=None, rows_per_vec=1, res1=None, a_res1=1.0, res2=None, a_res2=1.0, a_acc=1.0,
+            geglu=False, act=0):
+    """Fused epilogue descriptor; `out`/`res*` are 2-D [rows, cols] views (row stride = leading dimension)."""
+    _need_cuda(out, bias, rowvec, res1, res2)
+    e = Epilogue()
+    e.bias = None if bias is None else bias.data_ptr()
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    e.rowvec = None if rowvec is None else rowvec.data_ptr()
+    if rowvec is not None:
+        assert rowvec.dtype == torch.float32 and rowvec.dim() == 2 and rowvec.stride(1) == 1
+        e.ld_rowvec = rowvec.stride(0)
+    e.rows_per_vec = int(rows_per_vec)
+    if res1 is not None:
+        e.res1, e.ld_res1, e.res1_f32 = res1.data_ptr(), _ld(res1), _is_f32(res1)
+    if res2 is not None:
+        e.res2, e.ld_res2, e.res2_f32 = res2.data_ptr(), _ld(res2), _is_f32(res2)
+    e.a_acc, e.a_res1, e.a_res2 = float(a_acc), float(a_res1), float(a_res2)
+    e.out, e.ld_out, e.out_f32 = out.data_ptr(), _ld(out), _is_f32(out)
+    e.geglu, e.act = int(bool(geglu)), int(act)
+    return e
+
+
+def tc_run(A, C, in_ext, in_strides, out_ext, taps, W, ldw, N, ep, in_mul=1, gemm_tile=False, w_batch_stride=0):
+    _need_cuda(A, W)
+    assert A.dtype == act_dtype() and W.dtype == act_dtype(), (A.dtype, W.dtype)
+    op = TcOp()
+    op.A, op.C = A.data_ptr(), int(C)
+    op.Xi, op.Yi, op.Zi = [int(v) for v in in_ext]
+    op.sx, op.sy, op.sz = [int(v) for v in in_strides]
+    op.Xo, op.Yo, op.Zo = [int(v) for v in out_ext]
+    op.in_mul, op.ntaps = int(in_mul), len(taps)
+    for i, (dx, dy, dz) in enumerate(taps):
+        op.tap_dx[i], op.tap_dy[i], op.tap_dz[i] = dx, dy, dz
+    op.gemm_tile = int(bool(gemm_tile))
+    op.W, op.ldw, op.w_batch_stride, op.N = W.data_ptr(), int(ldw), int(w_batch_stride), int(N)
+    op.ep = ep
+    check(lib().gcd_tc_run(ctypes.byref(op), _stream()), "gcd_tc_run")
+
+
+def linear(x, w, ep):
+    """x: act [rows, K] (row stride arbitrary multiple of 8), w: act [N, K]. nn.Linear / 1x1 conv."""
+    rows, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and w.stride(1) == 1 and x.stride(1) == 1
+    sx = x.stride(0)
+    tc_run(x, K, (rows, 1, 1), (sx, sx * rows, sx * rows), (rows, 1, 1), [(0, 0, 0)], w, w.stride(0), N, ep,
+           gemm_tile=True)
+
+
+def bmm_nt(a, b, ep):
+    """a: act [G, M, K], b: act [G, N, K] -> out rows g*M+m, cols n  (torch.bmm(a, b.transpose(1,2)))."""
+    G, M, K = a.shape
+    N = b.shape[1]
+    assert b.shape[0] == G and b.shape[2] == K and a.stride(2) == 1 and b.stride(2) == 1
+    tc_run(a, K, (M, G, 1), (a.stride(1), a.stride(0), a.stride(0) * G), (M, G, 1), [(0, 0, 0)], b, b.stride(1), N, ep,
+           gemm_tile=True, w_batch_stride=b.stride(0))
+
+
+TAPS_3x3 = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+TAPS_T3 = [(0, kt - 1, 0) for kt in range(3)]
+
+
+def conv2d_3x3(x, w, ep, stride=1):
+    """x: act [n, H, W, C] channels-last contiguous; w: act [Cout, 9*C] packed (ky, kx, c). padding 1."""
+    n, H, W_, C = x.shape
+    assert x.is_contiguous() and w.shape[1] == 9 * C
+    Ho = (H - 1) // stride + 1
+    Wo = (W_ - 1) // stride + 1
+    tc_run(x, C, (W_, H, n), (C, W_ * C, H * W_ * C), (Wo, Ho, n), TAPS_3x3, w, w.stride(0), w.shape[0], ep,
+           in_mul=stride)
+    return Ho, Wo
+
+
+def conv_t3(x, w, ep):
+    """x: act [B, T, HW, C] contiguous; w: act [Cout, 3*C] packed (kt, c). Conv3d kernel (3,1,1), padding (1,0,0)."""
+    B, T, HW, C = x.shape
+    assert x.is_contiguous() and w.shape[1] == 3 * C
+    tc_run(x, C, (HW, T, B), (C, HW * C, T * HW * C), (HW, T, B), TAPS_T3, w, w.stride(0), w.shape[0], ep)
+
+
+# ------------------------------------------------------------------------------------------------ norms
+def groupnorm(x, n_img, rows, C, gamma, beta, eps, silu, out, stats, groups=32):
+    """x: [n_img*rows, C] float32 or act -> out act. stats: float64 scratch [n_img*groups*2]."""
+    _need_cuda(x, gamma, beta, out, stats)
+    L = lib()
+    st = _stream()
+    nbytes = n_img * groups * 2 * 8
+    assert stats.dtype == torch.float64 and stats.numel() * 8 >= nbytes
+    f32 = _is_f32(x)
+    check(L.gcd_memset_async(_p(stats), 0, nbytes, st), "memset")
+    check(L.gcd_groupnorm_stats(_p(x), f32, n_img, rows, C, groups, _p(stats), st), "groupnorm_stats")
+    check(L.gcd_groupnorm_apply(_p(x), f32, n_img, rows, C, groups, _p(stats), _p(gamma), _p(beta), float(eps),
+                                int(bool(silu)), _p(out), st), "groupnorm_apply")
+
+
+def layernorm(x, gamma, beta, out, eps=1e-5, add=None, add_rows_per=1, add_mod=1, sum_out=None):
+    _need_cuda(x, gamma, beta, out, add, sum_out)
+    rows, C = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == act_dtype()
+    check(lib().gcd_layernorm(_p(x), rows, C, _p(gamma), _p(beta), float(eps), _p(add), int(add_rows_per), int(add_mod),
+                              _p(sum_out), _p(out), _stream()), "layernorm")
+
+
+def softmax_rows(x, scale, out):
+    _need_cuda(x, out)
+    rows, cols = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    check(lib().gcd_softmax_rows(_p(x), rows, cols, float(scale), _p(out), _stream()), "softmax_rows")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attention_spatial(qkv, frames, tokens, heads, out):
+    _need_cuda(qkv, out)
+    assert qkv.dtype == act_dtype() and qkv.is_contiguous() and out.is_contiguous()
+    check(lib().gcd_attention_spatial(_p(qkv), frames, tokens, heads, _p(out), _stream()), "attention_spatial")
+
+
+def attention_temporal(qkv, clips, T, tokens, heads, out):
+    _need_cuda(qkv, out)
+    assert qkv.dtype == act_dtype() and qkv.is_contiguous() and out.is_contiguous()
+    check(lib().gcd_attention_temporal(_p(qkv), clips, T, tokens, heads, _p(out), _stream()), "attention_temporal")
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def cast_to_act(x, out):
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    check(lib().gcd_cast_f32_to_act(_p(x), x.numel(), _p(out), _stream()), "cast")
+
+
+def upsample2x_to_act(x, n, H, W, C, out):
+    _need_cuda(x, out)
+    check(lib().gcd_upsample2x_to_act(_p(x), n, H, W, C, _p(out), _stream()), "upsample2x")
+
+
+def concat_channels(a, b, out):
+    _need_cuda(a, b, out)
+    rows = a.shape[0]
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    check(lib().gcd_concat_channels(_p(a), a.shape[1], _p(b), b.shape[1], rows, _p(out), _stream()), "concat")
+
+
+def silu_act(x, out):
+    _need_cuda(x, out)
+    check(lib().gcd_silu_act(_p(x), x.numel(), _p(out), _stream()), "silu")
+
+
+def timestep_embedding(t, dim, out_act=None, out_f32=None, max_period=10000.0):
+    _need_cuda(t, out_act, out_f32)
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    check(lib().gcd_timestep_embedding(_p(t), t.numel(), dim, float(max_period), _p(out_act), _p(out_f32), _stream()),
+          "timestep_embedding")
+
+
+def sampler_prep(x, uc_concat, c_concat, BT, H, W, c_in, out):
+    _need_cuda(x, uc_concat, c_concat, out)
+    check(lib().gcd_sampler_prep(_p(x), _p(uc_concat), _p(c_concat), BT, H, W, float(c_in), _p(out), _stream()),
+          "sampler_prep")
+
+
+def sampler_update(x, net_out, ld_net, BT, T, H, W, c_out, c_skip, sigma, dt, scale):
+    _need_cuda(x, net_out, scale)
+    check(lib().gcd_sampler_update(_p(x), _p(net_out), ld_net, BT, T, H, W, float(c_out), float(c_skip), float(sigma),
+                                   float(dt), _p(scale), _stream()), "sampler_update")
+
+
+def launch_count():
+    return int(lib().gcd_launch_count())
