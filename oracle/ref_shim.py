@@ -1,0 +1,66 @@
+"""Imports the reference's own hot-path modules from /root/reference (build container only; TEST INFRASTRUCTURE).
+
+`import sgm` fails upstream (needs pytorch_lightning / omegaconf / open_clip / kornia, absent here — SURVEY.md §8(c)),
+so empty package shells named `sgm`, `sgm.modules`, `sgm.models` are pre-registered with __path__ pointing at the
+reference tree (their __init__.py never runs) plus a stub `omegaconf` (type hints only, sampling.py:9).
+"""
+import os
+import sys
+import types
+
+REF = "/root/reference/gcd-model"
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "sgm"))
+
+
+def install():
+    if "sgm" in sys.modules and getattr(sys.modules["sgm"], "_gcd_shim", False):
+        return
+    if not available():
+        raise RuntimeError("reference tree not present (only available in the build container)")
+    for name, sub in (("sgm", "sgm"), ("sgm.modules", "sgm/modules"), ("sgm.models", "sgm/models"),
+                      ("sgm.modules.autoencoding", "sgm/modules/autoencoding"),
+                      ("sgm.modules.diffusionmodules", "sgm/modules/diffusionmodules")):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF, sub)]
+        m._gcd_shim = True
+        sys.modules[name] = m
+    if "omegaconf" not in sys.modules:
+        oc = types.ModuleType("omegaconf")
+        oc.ListConfig = list
+        oc.OmegaConf = type("OmegaConf", (), {})
+        oc.DictConfig = dict
+        sys.modules["omegaconf"] = oc
+
+
+def build_ref_unet(cfg):
+    """Reference VideoUNet (video_model.py:84) on CPU with *uninitialised* storage; caller loads a state dict."""
+    install()
+    import torch
+    from sgm.modules.diffusionmodules.video_model import VideoUNet
+    kw = dict(adm_in_channels=cfg["adm_in_channels"], num_classes="sequential", use_checkpoint=False,
+              in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], model_channels=cfg["model_channels"],
+              attention_resolutions=cfg["attention_resolutions"], num_res_blocks=cfg["num_res_blocks"],
+              channel_mult=cfg["channel_mult"], num_head_channels=cfg["num_head_channels"],
+              use_linear_in_transformer=True, transformer_depth=cfg["transformer_depth"],
+              context_dim=cfg["context_dim"], spatial_transformer_attn_type="softmax", extra_ff_mix_layer=True,
+              use_spatial_context=True, merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1],
+              aux_emb_dim=cfg["aux_emb_dim"], aux_zero_init=False)
+    with torch.device("meta"):
+        net = VideoUNet(**kw)
+    net = net.to_empty(device="cpu")
+    return net.eval()
+
+
+def build_ref_decoder(cfg):
+    install()
+    import torch
+    from sgm.modules.autoencoding.temporal_ae import VideoDecoder
+    kw = dict(attn_type="vanilla", double_z=True, z_channels=cfg["z_channels"], resolution=256, in_channels=3,
+              out_ch=cfg["out_ch"], ch=cfg["ch"], ch_mult=cfg["ch_mult"], num_res_blocks=cfg["num_res_blocks"],
+              attn_resolutions=[], dropout=0.0, video_kernel_size=[3, 1, 1])
+    with torch.device("meta"):
+        dec = VideoDecoder(**kw)
+    return dec.to_empty(device="cpu").eval()

@@ -228,3 +228,15 @@ def test_sampler_kernels(ops):
     d = du + sc * (dc - du)
     ref = x + (sigma_next - sigma) * (x - d) / sigma
     assert (xn - ref).abs().max() < 1e-4 * ref.abs().max()
+
+
+@pytest.mark.parametrize("frames,tokens,heads", [(2, 256, 5), (3, 144, 20), (1, 576, 10), (2, 100, 5), (1, 2304, 5), (2, 4, 5)])
+def test_attention_spatial(ops, frames, tokens, heads):
+    AD = ops.act_dtype()
+    C = heads * 64
+    qkv = rnd(frames, tokens, 3 * C, dtype=AD, scale=1.5)
+    out = torch.empty(frames, tokens, C, device="cuda", dtype=AD)
+    ops.attention_spatial(qkv, frames, tokens, heads, out)
+    q, k, v = qkv.float().view(frames, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(frames, tokens, C)
+    assert relerr(out, ref) < 3e-3
