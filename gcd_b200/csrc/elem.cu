@@ -155,3 +155,50 @@ extern "C" int gcd_sampler_update(float* x, const float* net_out, int ld_net, in
               dt, scale);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ layout glue
+// NCHW float32 [N, C, HW] -> channels-last act [N, HW, Cpad] (channels >= C zero-filled); one thread per 8 out channels
+__global__ void nchw_to_act_nhwc_kernel(const float* __restrict__ in, int N, int C, int HW, int Cpad,
+                                        act_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g8 = Cpad / 8;
+    if (i >= (int64_t)N * HW * g8) return;
+    int g = (int)(i % g8);
+    int64_t pix = i / g8;
+    int hw = (int)(pix % HW);
+    int n = (int)(pix / HW);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int c = g * 8 + j;
+        v[j] = c < C ? in[((int64_t)n * C + c) * HW + hw] : 0.f;
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+extern "C" int gcd_nchw_to_act_nhwc(const float* in, int N, int C, int HW, int Cpad, void* out, void* stream) {
+    GCD_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "nchw_to_act_nhwc: bad Cpad");
+    LAUNCH_1D(nchw_to_act_nhwc_kernel, (int64_t)N * HW * (Cpad / 8), stream, in, N, C, HW, Cpad, (act_t*)out);
+    return 0;
+}
+// channels-last float32 [N, HW, ld] (first C columns) -> NCHW float32 [N, C, HW]
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int ld, int N, int C, int HW, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * C * HW) return;
+    int hw = (int)(i % HW);
+    int64_t t = i / HW;
+    int c = (int)(t % C);
+    int n = (int)(t / C);
+    out[i] = in[((int64_t)n * HW + hw) * ld + c];
+}
+extern "C" int gcd_nhwc_to_nchw_f32(const float* in, int ld, int N, int C, int HW, float* out, void* stream) {
+    LAUNCH_1D(nhwc_to_nchw_kernel, (int64_t)N * C * HW, stream, in, ld, N, C, HW, out);
+    return 0;
+}
+__global__ void silu_f32_to_act_kernel(const float* __restrict__ in, int64_t n, act_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = f2act(ptx::silu(in[i]));
+}
+extern "C" int gcd_silu_f32_to_act(const float* in, int64_t n, void* out, void* stream) {
+    LAUNCH_1D(silu_f32_to_act_kernel, n, stream, in, n, (act_t*)out);
+    return 0;
+}

@@ -104,84 +104,126 @@ template <int BN>
 struct TcCfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STAGES = (BN == 256) ? 4 : 5;
+    static constexpr int EPI_LD = 36;                       // floats per staged row (32 + 4 pad: conflict-free)
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // one 32x32 fp32 chunk per epilogue warp
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <bool OUT_F32>
-__device__ __forceinline__ void store_run(void* out, int64_t off, const float* x, int n, bool vec) {
-    if (OUT_F32) {
-        float* o = reinterpret_cast<float*>(out) + off;
-        if (vec) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                if (j < n) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-        } else {
-            for (int j = 0; j < n; j++) o[j] = x[j];
-        }
-    } else {
-        act_t* o = reinterpret_cast<act_t*>(out) + off;
-        if (vec) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 8)
-                if (j < n)
-                    *reinterpret_cast<uint4*>(o + j) = make_uint4(pack2(x[j], x[j + 1]), pack2(x[j + 2], x[j + 3]),
-                                                                  pack2(x[j + 4], x[j + 5]), pack2(x[j + 6], x[j + 7]));
-        } else {
-            for (int j = 0; j < n; j++) o[j] = f2act(x[j]);
-        }
-    }
-}
-
-// add a_res * R[off .. off+16) into x (16 values, n valid)
-__device__ __forceinline__ void add_res16(float* x, const void* R, int64_t off, bool f32, float a, int n, bool vec) {
+// ---- coalesced epilogue helpers: a lane owns 4 consecutive output columns of one row -------------------------
+__device__ __forceinline__ void load_res4(float* x, const void* R, int64_t off, bool f32, float a, int nv, bool vec) {
     if (f32) {
         const float* r = reinterpret_cast<const float*>(R) + off;
         if (vec) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                float4 t = *reinterpret_cast<const float4*>(r + j);
-                x[j] += a * t.x; x[j + 1] += a * t.y; x[j + 2] += a * t.z; x[j + 3] += a * t.w;
-            }
+            float4 t = *reinterpret_cast<const float4*>(r);
+            x[0] += a * t.x; x[1] += a * t.y; x[2] += a * t.z; x[3] += a * t.w;
         } else {
-            for (int j = 0; j < n; j++) x[j] += a * r[j];
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < nv) x[j] += a * r[j];
         }
     } else {
         const act_t* r = reinterpret_cast<const act_t*>(R) + off;
         if (vec) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-                uint4 t = *reinterpret_cast<const uint4*>(r + j);
-                float2 f;
-                f = unpack2(t.x); x[j] += a * f.x; x[j + 1] += a * f.y;
-                f = unpack2(t.y); x[j + 2] += a * f.x; x[j + 3] += a * f.y;
-                f = unpack2(t.z); x[j + 4] += a * f.x; x[j + 5] += a * f.y;
-                f = unpack2(t.w); x[j + 6] += a * f.x; x[j + 7] += a * f.y;
-            }
+            uint2 t = *reinterpret_cast<const uint2*>(r);
+            float2 f0 = unpack2(t.x), f1 = unpack2(t.y);
+            x[0] += a * f0.x; x[1] += a * f0.y; x[2] += a * f1.x; x[3] += a * f1.y;
         } else {
-            for (int j = 0; j < n; j++) x[j] += a * act2f(r[j]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < nv) x[j] += a * act2f(r[j]);
+        }
+    }
+}
+__device__ __forceinline__ void store4(void* out, int64_t off, bool f32, const float* x, int nv, bool vec) {
+    if (f32) {
+        float* o = reinterpret_cast<float*>(out) + off;
+        if (vec) *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < nv) o[j] = x[j];
+        }
+    } else {
+        act_t* o = reinterpret_cast<act_t*>(out) + off;
+        if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack2(x[0], x[1]), pack2(x[2], x[3]));
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < nv) o[j] = f2act(x[j]);
         }
     }
 }
 
-// Finishes 16 consecutive output columns [ncol, ncol+16) of one row: act, blend with residuals, store.
-__device__ __forceinline__ void finish16(const TcParams& p, float* x, int64_t row, int ncol, int nvalid) {
-    if (nvalid <= 0) return;
-    const bool vec = p.vec_ok && nvalid >= 16;
-    if (p.act == 1) {
+// One 32-accumulator-column chunk of one warp's 32 rows, read back from the staging tile in coalesced order.
+// LPR lanes cover one row (4 output columns per lane); LPR = 8 (plain) or 4 (GEGLU: 16 value + 16 gate columns).
+// Phase 1 issues every residual load of the chunk (memory-level parallelism), phase 2 computes and stores.
+template <int LPR>
+__device__ __forceinline__ void epi_chunk(const TcParams& p, const float* stg, int ld, int q, int lane, int nbase,
+                                          int tx, int ty, int tz, int TW, int TH, int TN) {
+    constexpr int RPS = 32 / LPR, STEPS = LPR;
+    constexpr bool GEGLU = (LPR == 4);
+    const int c4 = (lane % LPR) * 4;
+    const int rsub = lane / LPR;
+    const int Nout = GEGLU ? (p.N >> 1) : p.N;
+    const int n = nbase + c4;                                  // accumulator (value) column of this lane
+    const int ncol = GEGLU ? (nbase >> 1) + c4 : n;            // output column
+    const int nv = Nout - ncol;
+    if (nv <= 0) return;
+    const bool vec = p.vec_ok && nv >= 4;
+    float bv[4] = {0.f, 0.f, 0.f, 0.f}, bg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) x[j] = silu(x[j]);
+        for (int j = 0; j < 4; j++) {
+            if (n + j < p.N) bv[j] = __ldg(p.bias + n + j);
+            if (GEGLU) bg[j] = __ldg(p.bias + n + 16 + j);
+        }
     }
-    if (p.a0 != 1.0f) {
+    int64_t rows[STEPS];
+    float r1v[STEPS][4], r2v[STEPS][4];
 #pragma unroll
-        for (int j = 0; j < 16; j++) x[j] *= p.a0;
+    for (int s = 0; s < STEPS; s++) {
+        const int r = q * 32 + s * RPS + rsub;
+        const int x = tx * TW + (r & (TW - 1));
+        const int y = ty * TH + ((r >> p.lTW) & (TH - 1));
+        const int z = tz * TN + (r >> (p.lTW + p.lTH));
+        const bool valid = (x < p.Xo) && (y < p.Yo) && (z < p.Zo);
+        rows[s] = valid ? ((int64_t)z * p.Yo + y) * p.Xo + x : -1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { r1v[s][j] = 0.f; r2v[s][j] = 0.f; }
+        if (valid) {
+            if (p.r1) load_res4(r1v[s], p.r1, rows[s] * p.ld1 + ncol, p.r1f32, p.a1, nv, vec);
+            if (p.r2) load_res4(r2v[s], p.r2, rows[s] * p.ld2 + ncol, p.r2f32, p.a2, nv, vec);
+        }
     }
-    if (p.r1) add_res16(x, p.r1, row * p.ld1 + ncol, p.r1f32, p.a1, nvalid, vec);
-    if (p.r2) add_res16(x, p.r2, row * p.ld2 + ncol, p.r2f32, p.a2, nvalid, vec);
-    if (p.of32)
-        store_run<true>(p.out, row * p.ldo + ncol, x, nvalid, vec);
-    else
-        store_run<false>(p.out, row * p.ldo + ncol, x, nvalid, vec);
+#pragma unroll
+    for (int s = 0; s < STEPS; s++) {
+        if (rows[s] < 0) continue;
+        const int rl = s * RPS + rsub;
+        float xf[4];
+        {
+            float4 t = *reinterpret_cast<const float4*>(stg + rl * ld + c4);
+            xf[0] = t.x + bv[0]; xf[1] = t.y + bv[1]; xf[2] = t.z + bv[2]; xf[3] = t.w + bv[3];
+        }
+        const float* rv = p.rowvec ? p.rowvec + (rows[s] / p.rpv) * (int64_t)p.ldv + n : nullptr;
+        if (rv) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (n + j < p.N) xf[j] += __ldg(rv + j);
+        }
+        if (GEGLU) {
+            float4 g = *reinterpret_cast<const float4*>(stg + rl * ld + 16 + c4);
+            float gg[4] = {g.x + bg[0], g.y + bg[1], g.z + bg[2], g.w + bg[3]};
+            if (rv) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) gg[j] += __ldg(rv + 16 + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) xf[j] *= gelu_erf(gg[j]);
+        }
+        if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) xf[j] = silu(xf[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) xf[j] = p.a0 * xf[j] + r1v[s][j] + r2v[s][j];
+        store4(p.out, rows[s] * p.ldo + ncol, p.of32, xf, nv, vec);
+    }
 }
 
 template <int BN>
@@ -192,7 +234,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+    float* sEpi = reinterpret_cast<float*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::EPI_BYTES);
     uint64_t* full = bars;                       // [STAGES]
     uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
     uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]
@@ -284,9 +327,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
+        // TMEM rows arrive one-per-thread; each 32-column chunk is transposed through a per-warp smem tile so that
+        // global loads/stores are coalesced: a lane then owns 4 consecutive columns, LPR lanes cover one row.
         const int q = warp & 3;              // TMEM lane quadrant of this warp
-        const int r = q * 32 + lane;         // tile row handled by this thread
-        const int Nout = p.geglu ? (p.N >> 1) : p.N;
+        float* stg = sEpi + q * 32 * Cfg::EPI_LD;
         int it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
             const int as = it & 1;
@@ -296,12 +340,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int tx = mt % p.ntx;
             const int ty = (mt / p.ntx) % p.nty;
             const int tz = mt / (p.ntx * p.nty);
-            const int x = tx * TW + (r & (TW - 1));
-            const int y = ty * TH + ((r >> p.lTW) & (TH - 1));
-            const int z = tz * TN + (r >> (p.lTW + p.lTH));
-            const bool valid = (x < p.Xo) && (y < p.Yo) && (z < p.Zo);
-            const int64_t row = ((int64_t)z * p.Yo + y) * p.Xo + x;
-            const float* rv = (p.rowvec && valid) ? p.rowvec + (row / p.rpv) * (int64_t)p.ldv : nullptr;
             const int n0 = nt * BN;
 
             mbar_wait(&tfull[as], aphase);
@@ -312,44 +350,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
-                const int n = n0 + c0;
-                if (valid && n < p.N) {
-                    float xf[32];
+                if (n0 + c0 >= p.N) continue;     // warp-uniform
+                {
+                    float4* dst = reinterpret_cast<float4*>(stg + lane * Cfg::EPI_LD);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) xf[j] = __uint_as_float(v[j]);
-                    const int nv = min(32, p.N - n);
-                    if (p.bias) {
-                        if (nv == 32 && p.vec_ok) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                                xf[j] += b.x; xf[j + 1] += b.y; xf[j + 2] += b.z; xf[j + 3] += b.w;
-                            }
-                        } else {
-                            for (int j = 0; j < nv; j++) xf[j] += p.bias[n + j];
-                        }
-                    }
-                    if (rv) {
-                        if (nv == 32 && (p.ldv & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 b = __ldg(reinterpret_cast<const float4*>(rv + n + j));
-                                xf[j] += b.x; xf[j + 1] += b.y; xf[j + 2] += b.z; xf[j + 3] += b.w;
-                            }
-                        } else {
-                            for (int j = 0; j < nv; j++) xf[j] += rv[n + j];
-                        }
-                    }
-                    if (p.geglu) {
-                        float g[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) g[j] = xf[j] * gelu_erf(xf[16 + j]);
-                        finish16(p, g, row, n >> 1, min(16, Nout - (n >> 1)));
-                    } else {
-                        finish16(p, xf, row, n, min(16, Nout - n));
-                        finish16(p, xf + 16, row, n + 16, min(16, Nout - n - 16));
-                    }
+                    for (int j = 0; j < 8; j++)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 }
+                __syncwarp();
+                if (p.geglu) epi_chunk<4>(p, stg, Cfg::EPI_LD, q, lane, n0 + c0, tx, ty, tz, TW, TH, TN);
+                else         epi_chunk<8>(p, stg, Cfg::EPI_LD, q, lane, n0 + c0, tx, ty, tz, TW, TH, TN);
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);

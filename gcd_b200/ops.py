@@ -198,6 +198,24 @@ def silu_act(x, out):
     check(lib().gcd_silu_act(_p(x), x.numel(), _p(out), _stream()), "silu")
 
 
+def silu_f32_to_act(x, out):
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32
+    check(lib().gcd_silu_f32_to_act(_p(x), x.numel(), _p(out), _stream()), "silu_f32")
+
+
+def nchw_to_act_nhwc(x, N, C, HW, Cpad, out):
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(lib().gcd_nchw_to_act_nhwc(_p(x), N, C, HW, Cpad, _p(out), _stream()), "nchw_to_act_nhwc")
+
+
+def nhwc_to_nchw(x, ld, N, C, HW, out):
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
+    check(lib().gcd_nhwc_to_nchw_f32(_p(x), ld, N, C, HW, _p(out), _stream()), "nhwc_to_nchw")
+
+
 def timestep_embedding(t, dim, out_act=None, out_f32=None, max_period=10000.0):
     _need_cuda(t, out_act, out_f32)
     assert t.dtype == torch.float32 and t.is_contiguous()

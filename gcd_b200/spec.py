@@ -184,3 +184,22 @@ def decoder_param_shapes(cfg):
             _wb(d, "conv_out", cout, cin, 3, 3)
             _wb(d, "conv_out.time_mix_conv", cout, cout, 3, 1, 1)
     return d
+
+
+def unet_ctor_kwargs(cfg):
+    """Constructor kwargs of VideoUNet as written in the GCD YAML (configs/infer_kubric.yaml:21-40)."""
+    return dict(adm_in_channels=cfg["adm_in_channels"], num_classes="sequential", use_checkpoint=True,
+                in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], model_channels=cfg["model_channels"],
+                attention_resolutions=cfg["attention_resolutions"], num_res_blocks=cfg["num_res_blocks"],
+                channel_mult=cfg["channel_mult"], num_head_channels=cfg["num_head_channels"],
+                use_linear_in_transformer=True, transformer_depth=cfg["transformer_depth"], context_dim=cfg["context_dim"],
+                spatial_transformer_attn_type="softmax-xformers", extra_ff_mix_layer=True, use_spatial_context=True,
+                merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1], aux_emb_dim=cfg["aux_emb_dim"],
+                aux_zero_init=False)
+
+
+def decoder_ctor_kwargs(cfg):
+    """Constructor kwargs of VideoDecoder as in configs/infer_kubric.yaml:152-164."""
+    return dict(attn_type="vanilla", double_z=True, z_channels=cfg["z_channels"], resolution=256, in_channels=3,
+                out_ch=cfg["out_ch"], ch=cfg["ch"], ch_mult=cfg["ch_mult"], num_res_blocks=cfg["num_res_blocks"],
+                attn_resolutions=[], dropout=0.0, video_kernel_size=[3, 1, 1])

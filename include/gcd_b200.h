@@ -113,6 +113,13 @@ int gcd_upsample2x_to_act(const float* in, int n, int H, int W, int C, void* out
 int gcd_concat_channels(const float* a, int Ca, const float* b, int Cb, int64_t rows, float* out, void* stream);
 /* act(x) on act tensor: SiLU (emb_layers SiLU, openaimodel.py:262-268) */
 int gcd_silu_act(const void* in, int64_t n, void* out, void* stream);
+/* SiLU on a float32 tensor, written as act (emb_layers' nn.SiLU on `emb`, openaimodel.py:262-268) */
+int gcd_silu_f32_to_act(const float* in, int64_t n, void* out, void* stream);
+/* NCHW float32 [N,C,HW] -> channels-last act [N,HW,Cpad] (zero-padded channels): entry glue of VideoUNet.forward /
+ * VideoDecoder.forward when called through the plugin surface with torch NCHW tensors. */
+int gcd_nchw_to_act_nhwc(const float* in, int N, int C, int HW, int Cpad, void* out, void* stream);
+/* channels-last float32 [N,HW,ld] (first C columns) -> NCHW float32 [N,C,HW]: exit glue. */
+int gcd_nhwc_to_nchw_f32(const float* in, int ld, int N, int C, int HW, float* out, void* stream);
 /* timestep_embedding (util.py:207-231): t[n] float32 -> act [n, dim] = cat(cos, sin)(t * exp(-ln(max_period) k / half)) */
 int gcd_timestep_embedding(const float* t, int n, int dim, float max_period, void* out_act, float* out_f32,
                            void* stream);
