@@ -202,3 +202,36 @@ extern "C" int gcd_silu_f32_to_act(const float* in, int64_t n, void* out, void* 
     LAUNCH_1D(silu_f32_to_act_kernel, n, stream, in, n, (act_t*)out);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ VAE tail
+// AE3DConv.time_mix_conv (temporal_ae.py:86-107): Conv3d(3->3, kernel (3,1,1), padding (1,0,0)) over the frame axis of
+// the 3-channel conv_out result. in: channels-last float32 [B*T, HW, ld] (first 3 cols); out: NCHW float32 [B*T,3,HW].
+__global__ void vae_time_mix_kernel(const float* __restrict__ in, int ld, int B, int T, int HW,
+                                    const float* __restrict__ w /*[3][3][3] co,ci,kt*/, const float* __restrict__ b,
+                                    float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * T * HW) return;
+    int hw = (int)(i % HW);
+    int bt = (int)(i / HW);
+    int t = bt % T;
+    float acc[3] = {b[0], b[1], b[2]};
+#pragma unroll
+    for (int kt = 0; kt < 3; kt++) {
+        int tt = t + kt - 1;
+        if (tt < 0 || tt >= T) continue;
+        const float* px = in + ((int64_t)(bt + kt - 1) * HW + hw) * ld;
+#pragma unroll
+        for (int ci = 0; ci < 3; ci++) {
+            float v = px[ci];
+#pragma unroll
+            for (int co = 0; co < 3; co++) acc[co] += w[(co * 3 + ci) * 3 + kt] * v;
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < 3; co++) out[((int64_t)bt * 3 + co) * HW + hw] = acc[co];
+}
+extern "C" int gcd_vae_time_mix(const float* in, int ld, int B, int T, int HW, const float* w, const float* b, float* out,
+                                void* stream) {
+    LAUNCH_1D(vae_time_mix_kernel, (int64_t)B * T * HW, stream, in, ld, B, T, HW, w, b, out);
+    return 0;
+}

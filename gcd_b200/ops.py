@@ -216,6 +216,11 @@ def nhwc_to_nchw(x, ld, N, C, HW, out):
     check(lib().gcd_nhwc_to_nchw_f32(_p(x), ld, N, C, HW, _p(out), _stream()), "nhwc_to_nchw")
 
 
+def vae_time_mix(x, ld, B, T, HW, w, b, out):
+    _need_cuda(x, w, b, out)
+    check(lib().gcd_vae_time_mix(_p(x), ld, B, T, HW, _p(w), _p(b), _p(out), _stream()), "vae_time_mix")
+
+
 def timestep_embedding(t, dim, out_act=None, out_f32=None, max_period=10000.0):
     _need_cuda(t, out_act, out_f32)
     assert t.dtype == torch.float32 and t.is_contiguous()

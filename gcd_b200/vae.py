@@ -1,0 +1,225 @@
+"""B200-native temporal VAE decoder: drop-in for `sgm.modules.autoencoding.temporal_ae.VideoDecoder`
+(temporal_ae.py:293-349 over diffusionmodules/model.py:604-748), time_mode "conv-only" (the default, :302).
+
+`DiffusionEngine.decode_first_stage` gates on `isinstance(decoder, VideoDecoder)` (models/diffusion.py:242,620), so
+`VideoDecoder` here is built as a real subclass of the reference class whenever `sgm` is importable (its heavy
+__init__ is bypassed); standalone it is a plain nn.Module. State-dict keys equal the reference's
+(`first_stage_model.decoder.*`, gcd_b200/spec.py).
+
+Execution: channels-last, fp32 residual stream, 16-bit tensor-core operands, all compute in libgcd_b200.so kernels:
+3x3 / (3,1,1) convs = tcgen05 implicit GEMM with fused bias/residual/alpha-blend epilogues, GroupNorm+SiLU streaming
+kernels, the single-head d=512 mid attention as batched tcgen05 GEMMs (QK^T, PV) + a row-softmax kernel.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops, spec
+from .unet import BufferPool, register_param_tree
+
+
+class DecoderEngine:
+    def __init__(self, cfg, state, device):
+        self.cfg, self.device, self.AD = cfg, torch.device(device), ops.act_dtype()
+        self.pool = BufferPool(self.device)
+        self.plan = spec.decoder_plan(cfg)
+        self.w, self.alpha = {}, {}
+        self._pack(state)
+
+    def _pack(self, sd):
+        dev, AD, W = self.device, self.AD, self.w
+        g = lambda k: sd[k].detach().to(dev, torch.float32)
+
+        def conv3(name, key, cin_pad=None):
+            w = g(key + ".weight")
+            if cin_pad is not None and cin_pad != w.shape[1]:
+                w = torch.cat([w, w.new_zeros(w.shape[0], cin_pad - w.shape[1], 3, 3)], 1)
+            W[name + ".w"] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(AD).contiguous()
+            W[name + ".b"] = g(key + ".bias").contiguous()
+
+        def convt(name, key):
+            w = g(key + ".weight")[:, :, :, 0, 0]
+            W[name + ".w"] = w.permute(0, 2, 1).reshape(w.shape[0], -1).to(AD).contiguous()
+            W[name + ".b"] = g(key + ".bias").contiguous()
+
+        def conv1(name, key):
+            W[name + ".w"] = g(key + ".weight")[:, :, 0, 0].to(AD).contiguous()
+            W[name + ".b"] = g(key + ".bias").contiguous()
+
+        def norm(name, key):
+            W[name + ".g"], W[name + ".b"] = g(key + ".weight").contiguous(), g(key + ".bias").contiguous()
+
+        for kind, p, cin, cout in self.plan:
+            if kind == "conv_in":
+                conv3(p, p, cin_pad=64)
+            elif kind == "res":
+                norm(p + ".n1", p + ".norm1"); conv3(p + ".c1", p + ".conv1")
+                norm(p + ".n2", p + ".norm2"); conv3(p + ".c2", p + ".conv2")
+                if cin != cout:
+                    conv1(p + ".skip", p + ".nin_shortcut")
+                q = p + ".time_stack"
+                norm(q + ".n1", q + ".in_layers.0"); convt(q + ".c1", q + ".in_layers.2")
+                norm(q + ".n2", q + ".out_layers.0"); convt(q + ".c2", q + ".out_layers.3")
+                self.alpha[p] = float(torch.sigmoid(g(p + ".mix_factor")).item())
+            elif kind == "attn":
+                norm(p + ".norm", p + ".norm")
+                for n in ("q", "k", "v", "proj_out"):
+                    conv1(f"{p}.{n}", f"{p}.{n}")
+            elif kind == "up":
+                conv3(p, p + ".conv")
+            elif kind == "out":
+                norm("norm_out", "norm_out")
+                conv3("conv_out", "conv_out")
+                W["tmix.w"] = g("conv_out.time_mix_conv.weight").reshape(-1).contiguous()   # [co, ci, kt, 1, 1]
+                W["tmix.b"] = g("conv_out.time_mix_conv.bias").contiguous()
+        self.weight_bytes = sum(t.numel() * t.element_size() for t in W.values())
+
+    def _gn(self, x, n_img, rows, C, name, eps, silu, out):
+        st = self.pool.get("gn_stats", (max(n_img, 64) * 64,), torch.float64)
+        ops.groupnorm(x, n_img, rows, C, self.w[name + ".g"], self.w[name + ".b"], eps, silu, out, st)
+
+    def _res(self, p, x, cin, cout, n, B, T, H, Wd, tag):
+        """temporal_ae.VideoResBlock.forward (temporal_ae.py:64-83) over ResnetBlock.forward (model.py:127-151)."""
+        W, pool, AD = self.w, self.pool, self.AD
+        HW, rows = H * Wd, n * H * Wd
+        a = pool.get(f"a{cin}_{rows}", (rows, cin), AD)
+        self._gn(x, n, HW, cin, p + ".n1", 1e-6, True, a)
+        h1 = pool.get(f"h{cout}_{rows}", (rows, cout), AD)
+        ops.conv2d_3x3(a.view(n, H, Wd, cin), W[p + ".c1.w"], ops.make_ep(h1, bias=W[p + ".c1.b"]))
+        a2 = pool.get(f"a{cout}_{rows}", (rows, cout), AD)
+        self._gn(h1, n, HW, cout, p + ".n2", 1e-6, True, a2)
+        xs = pool.get(f"{tag}_{cout}_{rows}", (rows, cout), torch.float32)
+        if cin != cout:
+            xa = pool.get(f"xa{cin}_{rows}", (rows, cin), AD)
+            ops.cast_to_act(x, xa)
+            ops.linear(xa, W[p + ".skip.w"], ops.make_ep(xs, bias=W[p + ".skip.b"]))
+            res = xs
+        else:
+            res = x
+        ops.conv2d_3x3(a2.view(n, H, Wd, cout), W[p + ".c2.w"], ops.make_ep(xs, bias=W[p + ".c2.b"], res1=res))
+        q = p + ".time_stack"
+        self._gn(xs, B, T * HW, cout, q + ".n1", 1e-5, True, a2)
+        ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c1.w"], ops.make_ep(h1, bias=W[q + ".c1.b"]))
+        self._gn(h1, B, T * HW, cout, q + ".n2", 1e-5, True, a2)
+        # x = alpha * (x_s + conv) + (1 - alpha) * x_s = x_s + alpha * conv     (temporal_ae.py:79-80)
+        ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c2.w"],
+                    ops.make_ep(xs, bias=W[q + ".c2.b"], a_acc=self.alpha[p], res1=xs))
+        return xs
+
+    def _attn(self, p, x, C, n, S):
+        """AttnBlock (model.py:161-201): out = x + proj_out(softmax(q k^T / sqrt(C)) v), single head, per frame."""
+        W, pool, AD = self.w, self.pool, self.AD
+        rows = n * S
+        a = pool.get(f"a{C}_{rows}", (rows, C), AD)
+        self._gn(x, n, S, C, p + ".norm", 1e-6, False, a)
+        q = pool.get("attn_q", (rows, C), AD)
+        k = pool.get("attn_k", (rows, C), AD)
+        ops.linear(a, W[p + ".q.w"], ops.make_ep(q, bias=W[p + ".q.b"]))
+        ops.linear(a, W[p + ".k.w"], ops.make_ep(k, bias=W[p + ".k.b"]))
+        vt = pool.get("attn_vt", (n, C, S), AD)                       # V^T per frame (K-major operand of P.V)
+        for f in range(n):
+            ops.linear(W[p + ".v.w"], a[f * S:(f + 1) * S], ops.make_ep(vt[f]))
+        # chunk frames so the fp32 score matrix stays <= ~2.5 GB
+        fc = max(1, min(n, int(2.5e9 // (S * S * 4))))
+        o = pool.get("attn_o", (rows, C), AD)
+        for f0 in range(0, n, fc):
+            f1 = min(n, f0 + fc)
+            sc = pool.get("attn_s", (fc * S, S), torch.float32)[: (f1 - f0) * S]
+            pr = pool.get("attn_p", (fc * S, S), AD)[: (f1 - f0) * S]
+            ops.bmm_nt(q[f0 * S:f1 * S].view(f1 - f0, S, C), k[f0 * S:f1 * S].view(f1 - f0, S, C), ops.make_ep(sc))
+            ops.softmax_rows(sc, C ** -0.5, pr)
+            # softmax rows sum to 1 => the v bias contributes exactly +b_v to every output row
+            ops.bmm_nt(pr.view(f1 - f0, S, S), vt[f0:f1], ops.make_ep(o[f0 * S:f1 * S], bias=W[p + ".v.b"]))
+        ops.linear(o, W[p + ".proj_out.w"], ops.make_ep(x, bias=W[p + ".proj_out.b"], res1=x))
+        return x
+
+    def forward_cl(self, z_cl, n, H, Wd, T, out_nchw):
+        """z_cl: act channels-last [n, H, W, 64]; writes float32 NCHW [n, out_ch, 8H, 8W] into out_nchw."""
+        W, pool, AD = self.w, self.pool, self.AD
+        assert n % T == 0
+        B = n // T
+        h, hH, hW, hC = None, H, Wd, None
+        for i, (kind, p, cin, cout) in enumerate(self.plan):
+            rows = n * hH * hW
+            if kind == "conv_in":
+                h = pool.get(f"s0_{cout}_{rows}", (rows, cout), torch.float32)
+                ops.conv2d_3x3(z_cl, W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"]))
+                hC = cout
+            elif kind == "res":
+                h = self._res(p, h, cin, cout, n, B, T, hH, hW, f"s{1 + i % 2}")
+                hC = cout
+            elif kind == "attn":
+                h = self._attn(p, h, cin, n, hH * hW)
+            elif kind == "up":
+                xu = pool.get(f"up{cin}_{rows * 4}", (rows * 4, cin), AD)
+                ops.upsample2x_to_act(h, n, hH, hW, cin, xu)
+                hH, hW = 2 * hH, 2 * hW
+                h = pool.get(f"s0_{cout}_{rows * 4}", (rows * 4, cout), torch.float32)
+                ops.conv2d_3x3(xu.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"]))
+            elif kind == "out":
+                a = pool.get(f"a{cin}_{rows}", (rows, cin), AD)
+                self._gn(h, n, hH * hW, cin, "norm_out", 1e-6, True, a)
+                o16 = pool.get(f"out16_{rows}", (rows, 16), torch.float32)
+                ops.conv2d_3x3(a.view(n, hH, hW, cin), W["conv_out.w"], ops.make_ep(o16[:, :cout], bias=W["conv_out.b"]))
+                assert cout == 3, "AE3DConv tail kernel is written for 3 output channels"
+                ops.vae_time_mix(o16, 16, B, T, hH * hW, W["tmix.w"], W["tmix.b"], out_nchw)
+        return out_nchw
+
+
+def _reference_base():
+    try:
+        from sgm.modules.autoencoding.temporal_ae import VideoDecoder as Ref   # noqa: WPS433
+        return Ref
+    except Exception:
+        return nn.Module
+
+
+_Base = _reference_base()
+
+
+class VideoDecoder(_Base):
+    """Drop-in `target:` for sgm.modules.autoencoding.temporal_ae.VideoDecoder (ctor kwargs: infer_kubric.yaml:152-164)."""
+
+    def __init__(self, *args, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions=(), dropout=0.0,
+                 resamp_with_conv=True, in_channels=3, resolution=256, z_channels, give_pre_end=False, tanh_out=False,
+                 use_linear_attn=False, attn_type="vanilla", video_kernel_size=3, alpha=0.0, merge_strategy="learned",
+                 time_mode="conv-only", **ignorekwargs):
+        nn.Module.__init__(self)   # bypass the reference constructor (it would build the eager torch layers)
+
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(f"gcd_b200.VideoDecoder: unsupported option ({what}); only the GCD config is built")
+
+        need(time_mode == "conv-only" and merge_strategy == "learned", "time_mode/merge_strategy")
+        need(len(attn_resolutions) == 0 and attn_type in ("vanilla", "vanilla-xformers") and not use_linear_attn, "attention")
+        need(resamp_with_conv and not give_pre_end and not tanh_out and dropout == 0.0, "decoder flags")
+        need(list(video_kernel_size) == [3, 1, 1] if not isinstance(video_kernel_size, int) else False, "video_kernel_size")
+        need(out_ch == 3 and ch % 64 == 0, "out_ch must be 3, ch a multiple of 64")
+        self.cfg = dict(ch=ch, out_ch=out_ch, ch_mult=list(ch_mult), num_res_blocks=num_res_blocks, z_channels=z_channels)
+        self.time_mode, self.video_kernel_size, self.alpha, self.merge_strategy = time_mode, video_kernel_size, alpha, merge_strategy
+        register_param_tree(self, spec.decoder_param_shapes(self.cfg))
+        self._engine, self._engine_key = None, None
+
+    def get_last_layer(self, skip_time_mix=False, **kwargs):
+        return self.conv_out.time_mix_conv.weight if not skip_time_mix else self.conv_out.weight
+
+    def engine(self, device):
+        key = (str(device), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        if self._engine is None or self._engine_key != key:
+            self._engine = DecoderEngine(self.cfg, self.state_dict(), device)
+            self._engine_key = key
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, z, timesteps=None, skip_video=False, **kwargs):
+        if not z.is_cuda:
+            raise RuntimeError("gcd_b200.VideoDecoder runs on CUDA (sm_100a) only; there is no CPU path")
+        if skip_video or timesteps is None:
+            raise NotImplementedError("VideoDecoder needs timesteps=<frames per clip> and skip_video=False")
+        n, c, H, W = z.shape
+        eng = self.engine(z.device)
+        z_cl = eng.pool.get("z_cl", (n, H, W, 64), eng.AD)
+        ops.nchw_to_act_nhwc(z.to(torch.float32).contiguous(), n, c, H * W, 64, z_cl)
+        nup = len(self.cfg["ch_mult"]) - 1
+        out = torch.empty(n, self.cfg["out_ch"], H << nup, W << nup, device=z.device, dtype=torch.float32)
+        eng.forward_cl(z_cl, n, H, W, int(timesteps), out)
+        return out.to(z.dtype)

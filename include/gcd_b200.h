@@ -120,6 +120,10 @@ int gcd_silu_f32_to_act(const float* in, int64_t n, void* out, void* stream);
 int gcd_nchw_to_act_nhwc(const float* in, int N, int C, int HW, int Cpad, void* out, void* stream);
 /* channels-last float32 [N,HW,ld] (first C columns) -> NCHW float32 [N,C,HW]: exit glue. */
 int gcd_nhwc_to_nchw_f32(const float* in, int ld, int N, int C, int HW, float* out, void* stream);
+/* AE3DConv.time_mix_conv (temporal_ae.py:86-107): Conv3d(3->3,(3,1,1)) over frames of the VAE's 3-channel output.
+ * in: channels-last float32 [B*T, HW, ld] (first 3 columns); w: [3,3,3] (co,ci,kt); out: NCHW float32 [B*T,3,HW]. */
+int gcd_vae_time_mix(const float* in, int ld, int B, int T, int HW, const float* w, const float* b, float* out,
+                     void* stream);
 /* timestep_embedding (util.py:207-231): t[n] float32 -> act [n, dim] = cat(cos, sin)(t * exp(-ln(max_period) k / half)) */
 int gcd_timestep_embedding(const float* t, int n, int dim, float max_period, void* out_act, float* out_f32,
                            void* stream);
