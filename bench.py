@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — latent-frames/sec through the full GCD denoising hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload kubric|pardom|direct50]
+
+A "step" = one pass of the hot path over one batch: per GPU ONE clip of 14 latent frames, 72x128 (576x1024 px):
+25 EDM/Euler steps of the CFG-doubled SVD VideoUNet (28 frames per forward) + the temporal VAE decode of the 14 frames
+(BASELINE.json configs[1]; `direct50` = configs[3]: 50 steps, guider max scale 2.5). Clips are independent, so N GPUs run
+N clips (weak scaling) with one NCCL all_gather of the sampled latents per step. Synthetic inputs, seeded random weights
+(no checkpoints offline; zero-init tensors overwritten — gcd_b200/synthetic.py).
+
+JSON line (rank 0): `value` = whole-job latent-frames/s with inputs resident in HBM (CUDA-event timed, max over ranks);
+`e2e` = same metric through the public API gcd_b200.pipeline.GCDHotPath.sample_video with pinned HOST inputs and a
+device->host read of the decoded frames inside the timed region; `roofline` = tensor-core roofline of the dominant kernel
+class (tc_gemm implicit-GEMM conv/linear) from CUDA events on the launching stream + whole-path fraction; `cpu_baseline` =
+the CPU oracle port (oracle/gcd_oracle.py) timed on this box's host cores on a bounded sample.
+`--impl reference` times only that CPU port (the reference's own PyTorch code cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_FRAMES, LAT_H, LAT_W = 14, 72, 128
+WORKLOADS = {
+    "kubric": dict(unet="UNET_KUBRIC", steps=25, max_scale=1.5, name="Kubric-4D gradual max90, 25-step Euler sample, 14x72x128 latent (576x1024 px)"),
+    "pardom": dict(unet="UNET_PARDOM", steps=25, max_scale=1.5, name="ParallelDomain-4D gradual RGB, 25-step sample, 14x72x128 latent"),
+    "direct50": dict(unet="UNET_KUBRIC", steps=50, max_scale=2.5, name="Kubric-4D direct max180, CFG 2.5, 50-step sample, 14x72x128 latent"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d["bf16_tflops_sustained"], burst=d["bf16_tflops"], hbm=d["hbm_gbs"], src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        rows = [l.strip().split(", ") for l in self.f.read().strip().splitlines() if l.strip()]
+        rows = [r for r in rows if len(r) == 6 and r[0].isdigit()]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].strip() == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------------ CPU oracle leg
+def cpu_oracle_sample(unet_cfg, vae_cfg, steps, unet_state=None, vae_state=None, sample_hw=(16, 24), vae_hw=(8, 8),
+                      repeats=1):
+    """Times the CPU oracle port (restatement of the reference's PyTorch path) on a bounded sample and extrapolates to
+    the full workload by the exact algorithmic-FLOP ratio. Returns (latent_frames_per_s, description, cores)."""
+    from gcd_b200 import flops, spec, synthetic
+    from oracle import gcd_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if unet_state is None:
+        unet_state = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
+    if vae_state is None:
+        vae_state = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
+    h, w = sample_hw
+    x, c, uc, ioi = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, h, w)
+    n = 2 * T_FRAMES
+    xin = torch.cat((torch.cat([x, x]), torch.cat((uc["concat"], c["concat"]))), 1)
+    ctx = torch.cat((uc["crossattn"], c["crossattn"]))
+    y = torch.cat((uc["vector"], c["vector"]))
+    t = torch.full((n,), 0.5756)
+    z = torch.randn(T_FRAMES, 4, *vae_hw)
+    tu = tv = 1e30
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.unet_forward(unet_state, unet_cfg, xin, t, ctx, y, T_FRAMES, ioi)
+            tu = min(tu, time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            O.decode_first_stage(vae_state, vae_cfg, z, T_FRAMES)
+            tv = min(tv, time.perf_counter() - t0)
+    ru = flops.unet_forward_flops(unet_cfg, n, LAT_H, LAT_W) / flops.unet_forward_flops(unet_cfg, n, h, w)
+    rv = flops.decoder_flops(vae_cfg, T_FRAMES, LAT_H, LAT_W) / flops.decoder_flops(vae_cfg, T_FRAMES, *vae_hw)
+    full_s = steps * tu * ru + tv * rv
+    desc = (f"1 CFG UNet forward (28 frames) at latent {h}x{w} ({tu:.2f} s) + 1 VAE decode of 14 frames at latent "
+            f"{vae_hw[0]}x{vae_hw[1]} ({tv:.2f} s), fp32, {cores} threads; extrapolated to {steps} steps at 72x128 by "
+            f"algorithmic FLOP ratios x{ru:.1f} / x{rv:.1f}")
+    return T_FRAMES / full_s, desc, cores, tu + tv
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gcd_b200 import spec
+    unet_cfg, vae_cfg = getattr(spec, wl["unet"]), spec.VAE_DECODER
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, desc, cores, secs = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], sample_hw=(8, 16), vae_hw=(8, 8))
+        if i >= args.warmup:
+            vals.append((v, secs))
+    v = sum(x[0] for x in vals) / len(vals)
+    line = {"impl": "reference", "metric": "latent-frames/sec", "value": v, "unit": "latent-frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded random weights, random latents/conditioning)",
+            "config": {"workload": wl["name"], "impl_note": "CPU port of the reference PyTorch path (oracle/gcd_oracle.py); "
+                       "the reference itself is pure Python under /root/reference and cannot travel to the GPU box"},
+            "cpu_baseline": {"value": v, "unit": "latent-frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "latent-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ product arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kubric", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch.distributed as dist
+    from gcd_b200 import flops, ops, spec, synthetic
+    from gcd_b200.pipeline import GCDHotPath
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU port)")
+    ops.lib()  # fail loudly if libgcd_b200.so is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    unet_cfg, vae_cfg = getattr(spec, wl["unet"]), spec.VAE_DECODER
+    pipe = GCDHotPath(unet_cfg, vae_cfg, num_steps=wl["steps"], num_frames=T_FRAMES, max_scale=wl["max_scale"], device=dev)
+    ust = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
+    vst = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
+    pipe.load_state(ust, vst)
+    # rank r samples its own clip: seed 1234 + r (scripts/test.py:1059-1084 strides examples over workers the same way)
+    x0, c, uc, _ = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, LAT_H, LAT_W, seed=1234 + rank)
+    pin = lambda t: t.pin_memory()
+    hx, hc, huc = pin(x0), {k: pin(v) for k, v in c.items()}, {k: pin(v) for k, v in uc.items()}
+    dx, dc, duc = x0.to(dev), {k: v.to(dev) for k, v in c.items()}, {k: v.to(dev) for k, v in uc.items()}
+    h2d = sum(t.numel() * t.element_size() for t in [hx, *hc.values(), *huc.values()])
+    frames_host = torch.empty(T_FRAMES, 3, LAT_H * 8, LAT_W * 8, dtype=torch.float32).pin_memory()
+    d2h = frames_host.numel() * 4
+    gathered = [torch.empty(T_FRAMES, 4, LAT_H, LAT_W, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        z = pipe.sample_latents(dx.clone(), dc, duc)
+        fr = None if args.no_decode else pipe.decode_first_stage(z)
+        if world > 1:
+            dist.all_gather(gathered, z.contiguous())     # the path's only collective: final gather over NVLink
+        return z, fr
+
+    def step_e2e():
+        z, fr = pipe.sample_video(hx, hc, huc, decode=not args.no_decode)
+        if fr is not None:
+            frames_host.copy_(fr, non_blocking=True)
+        if world > 1:
+            dist.all_gather(gathered, z.contiguous())
+        torch.cuda.current_stream().synchronize()        # the caller holds the frames on the host when the step ends
+        return z
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = ops.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = ops.launch_count() - l0
+    clk = clocks.stop() if clocks else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    frames_total = world * args.steps * T_FRAMES
+    value = frames_total / (ms / 1e3)
+    e2e_value = frames_total / (ms_e2e / 1e3)
+
+    # ---- per-kernel-class roofline (one extra, untimed, instrumented step on rank 0)
+    line = None
+    if rank == 0:
+        pk = measured_peaks()
+        with ops.profile() as prof:
+            step_resident()
+        summ = prof.summary()
+        tc = summ.get("tc_gemm", dict(ms=1e-9, flops=0.0, launches=0))
+        tot_ms = sum(d["ms"] for d in summ.values())
+        tc_tflops = tc["flops"] / (tc["ms"] / 1e3) / 1e12
+        per_frame = flops.clip_flops(unet_cfg, vae_cfg, T_FRAMES, LAT_H, LAT_W, wl["steps"]) / T_FRAMES
+        path_tflops = per_frame * (value / world) / 1e12
+        roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv / linear)",
+                "achieved": round(tc_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(tc_tflops / pk["tflops"], 4),
+                "traffic": None, "peak_source": pk["src"],
+                "kernel_share_of_step": round(tc["ms"] / max(tot_ms, 1e-9), 4),
+                "whole_path": {"algorithmic_tflop_per_latent_frame": round(per_frame / 1e12, 1),
+                               "achieved": round(path_tflops, 1), "frac": round(path_tflops / pk["tflops"], 4)},
+                "classes": {k: {"ms": round(d["ms"], 2), "launches": d["launches"],
+                                "tflops": round(d["flops"] / max(d["ms"], 1e-9) / 1e9, 1),
+                                "gbs": round(d["bytes"] / max(d["ms"], 1e-9) / 1e6, 1)} for k, d in summ.items()}}
+        line = {"metric": "latent-frames/sec", "value": round(value, 4), "unit": "latent-frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 2),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if ops.lib().gcd_act_dtype() == 1 else "f16",
+                "data": "synthetic (seeded random weights of the named architecture, random latents/conditioning)",
+                "config": {"workload": wl["name"], "clips_per_gpu_per_step": 1, "latent": [T_FRAMES, 4, LAT_H, LAT_W],
+                           "sampler_steps": wl["steps"], "cfg_batch": 2 * T_FRAMES, "decode": not args.no_decode,
+                           "parallelism": f"clips x{world} (one NCCL all_gather of latents per step)" if world > 1 else "single GPU",
+                           "l2": "no explicit flush: per-step working set (3.2 GB fp16 weights + multi-GB activations) >> 126 MB L2",
+                           "precision": "fp16 tensor-core operands, fp32 accumulate / residual stream / norms"},
+                "e2e": {"value": round(e2e_value, 4), "unit": "latent-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": round(ms_e2e / args.steps, 2),
+                        "api": "gcd_b200.pipeline.GCDHotPath.sample_video(pinned host noise/cond) + frames -> pinned host"},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            v, desc, cores, _ = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], ust, vst)
+            line["cpu_baseline"] = {"value": v, "unit": "latent-frames/s", "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

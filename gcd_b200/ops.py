@@ -23,6 +23,53 @@ def act_dtype():
     return _ACT
 
 
+# ---- optional per-kernel-class timing (CUDA events on the launching stream); used by bench.py for `roofline` ----
+_PROF = None
+
+
+class profile:
+    """with ops.profile() as prof: ...  -> prof.summary() = {class: {ms, launches, flops, bytes}} (after a sync)."""
+
+    def __enter__(self):
+        global _PROF
+        self.recs = []
+        _PROF = self.recs
+        return self
+
+    def __exit__(self, *exc):
+        global _PROF
+        _PROF = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, fl, by in self.recs:
+            d = out.setdefault(name, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+class _timed:
+    __slots__ = ("name", "fl", "by", "e0")
+
+    def __init__(self, name, fl=0.0, by=0.0):
+        self.name, self.fl, self.by = name, fl, by
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _PROF is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROF.append((self.name, self.e0, e1, self.fl, self.by))
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -87,7 +134,8 @@ def tc_run(A, C, in_ext, in_strides, out_ext, taps, W, ldw, N, ep, in_mul=1, gem
     op.gemm_tile = int(bool(gemm_tile))
     op.W, op.ldw, op.w_batch_stride, op.N = W.data_ptr(), int(ldw), int(w_batch_stride), int(N)
     op.ep = ep
-    check(lib().gcd_tc_run(ctypes.byref(op), _stream()), "gcd_tc_run")
+    with _timed("tc_gemm", 2.0 * op.Xo * op.Yo * op.Zo * op.N * op.ntaps * op.C):
+        check(lib().gcd_tc_run(ctypes.byref(op), _stream()), "gcd_tc_run")
 
 
 def linear(x, w, ep):
@@ -140,18 +188,20 @@ def groupnorm(x, n_img, rows, C, gamma, beta, eps, silu, out, stats, groups=32):
     nbytes = n_img * groups * 2 * 8
     assert stats.dtype == torch.float64 and stats.numel() * 8 >= nbytes
     f32 = _is_f32(x)
-    check(L.gcd_memset_async(_p(stats), 0, nbytes, st), "memset")
-    check(L.gcd_groupnorm_stats(_p(x), f32, n_img, rows, C, groups, _p(stats), st), "groupnorm_stats")
-    check(L.gcd_groupnorm_apply(_p(x), f32, n_img, rows, C, groups, _p(stats), _p(gamma), _p(beta), float(eps),
-                                int(bool(silu)), _p(out), st), "groupnorm_apply")
+    with _timed("groupnorm", 0.0, n_img * rows * C * ((8 if f32 else 4) + 2)):
+        check(L.gcd_memset_async(_p(stats), 0, nbytes, st), "memset")
+        check(L.gcd_groupnorm_stats(_p(x), f32, n_img, rows, C, groups, _p(stats), st), "groupnorm_stats")
+        check(L.gcd_groupnorm_apply(_p(x), f32, n_img, rows, C, groups, _p(stats), _p(gamma), _p(beta), float(eps),
+                                    int(bool(silu)), _p(out), st), "groupnorm_apply")
 
 
 def layernorm(x, gamma, beta, out, eps=1e-5, add=None, add_rows_per=1, add_mod=1, sum_out=None):
     _need_cuda(x, gamma, beta, out, add, sum_out)
     rows, C = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == act_dtype()
-    check(lib().gcd_layernorm(_p(x), rows, C, _p(gamma), _p(beta), float(eps), _p(add), int(add_rows_per), int(add_mod),
-                              _p(sum_out), _p(out), _stream()), "layernorm")
+    with _timed("layernorm", 0.0, rows * C * (6 + (4 if sum_out is not None else 0))):
+        check(lib().gcd_layernorm(_p(x), rows, C, _p(gamma), _p(beta), float(eps), _p(add), int(add_rows_per),
+                                  int(add_mod), _p(sum_out), _p(out), _stream()), "layernorm")
 
 
 def softmax_rows(x, scale, out):
@@ -165,13 +215,15 @@ def softmax_rows(x, scale, out):
 def attention_spatial(qkv, frames, tokens, heads, out):
     _need_cuda(qkv, out)
     assert qkv.dtype == act_dtype() and qkv.is_contiguous() and out.is_contiguous()
-    check(lib().gcd_attention_spatial(_p(qkv), frames, tokens, heads, _p(out), _stream()), "attention_spatial")
+    with _timed("attn_spatial", 4.0 * frames * heads * tokens * tokens * 64, frames * tokens * heads * 64 * 8):
+        check(lib().gcd_attention_spatial(_p(qkv), frames, tokens, heads, _p(out), _stream()), "attention_spatial")
 
 
 def attention_temporal(qkv, clips, T, tokens, heads, out):
     _need_cuda(qkv, out)
     assert qkv.dtype == act_dtype() and qkv.is_contiguous() and out.is_contiguous()
-    check(lib().gcd_attention_temporal(_p(qkv), clips, T, tokens, heads, _p(out), _stream()), "attention_temporal")
+    with _timed("attn_temporal", 4.0 * clips * tokens * heads * T * T * 64, clips * T * tokens * heads * 64 * 8):
+        check(lib().gcd_attention_temporal(_p(qkv), clips, T, tokens, heads, _p(out), _stream()), "attention_temporal")
 
 
 # ------------------------------------------------------------------------------------------------ elementwise

@@ -1,0 +1,64 @@
+"""Hot-path driver: what DiffusionEngine.sample_video does between conditioning and pixels
+(models/diffusion.py:504-549): latent noise -> 25-step EDM/Euler sample (CFG) -> decode_first_stage (:233-251).
+This is the public API bench.py measures end to end and the object tests/smoke drive; under gcd-model/ the same
+classes are reached through `instantiate_from_config`."""
+import torch
+
+from . import sampling, spec
+from .unet import VideoUNet
+from .vae import VideoDecoder
+
+
+class GCDHotPath:
+    def __init__(self, unet_cfg=None, vae_cfg=None, num_steps=25, num_frames=14, max_scale=1.5, min_scale=1.0,
+                 sigma_max=700.0, scale_factor=0.18215, device="cuda"):
+        self.unet_cfg = dict(unet_cfg or spec.UNET_KUBRIC)
+        self.vae_cfg = dict(vae_cfg or spec.VAE_DECODER)
+        self.device = torch.device(device)
+        self.T, self.scale_factor = num_frames, scale_factor
+        self.unet = VideoUNet(**spec.unet_ctor_kwargs(self.unet_cfg))
+        self.decoder = VideoDecoder(**spec.decoder_ctor_kwargs(self.vae_cfg))
+        self.model = sampling.OpenAIWrapper(self.unet)
+        self.denoiser = sampling.Denoiser({"target": "gcd_b200.sampling.VScalingWithEDMcNoise"})
+        self.sampler = sampling.EulerEDMSampler(
+            discretization_config={"target": "gcd_b200.sampling.EDMDiscretization", "params": {"sigma_max": sigma_max}},
+            num_steps=num_steps,
+            guider_config={"target": "gcd_b200.sampling.LinearPredictionGuider",
+                           "params": {"num_frames": num_frames, "max_scale": max_scale, "min_scale": min_scale}},
+            device=str(self.device))
+
+    def load_state(self, unet_state, vae_state):
+        self.unet.load_state_dict(unet_state, strict=True)
+        self.decoder.load_state_dict(vae_state, strict=True)
+        self.unet.to(self.device)
+        self.decoder.to(self.device)
+        return self
+
+    @torch.no_grad()
+    def sample_latents(self, noise, c, uc, num_steps=None):
+        """noise: float32 [B*T,4,h,w] on device (consumed in place, sampling.py:54). c/uc: dicts of device tensors."""
+        BT = noise.shape[0]
+        extra = dict(num_video_frames=self.T,
+                     image_only_indicator=torch.zeros(2 * BT // self.T, self.T, device=noise.device))
+        den = sampling.FusedDenoiser(self.denoiser, self.model, **extra)
+        return self.sampler(den, noise, cond=c, uc=uc, num_steps=num_steps)
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, decoding_t=None):
+        """models/diffusion.py:233-251: z / scale_factor, chunks of `decoding_t` frames, fp32."""
+        z = z / self.scale_factor
+        n = decoding_t or self.T
+        outs = [self.decoder(z[i:i + n], timesteps=min(n, z.shape[0] - i)) for i in range(0, z.shape[0], n)]
+        return torch.cat(outs, 0)
+
+    @torch.no_grad()
+    def sample_video(self, noise, c, uc, num_steps=None, decode=True):
+        """Returns (latents [B*T,4,h,w], frames [B*T,3,8h,8w] or None). Host tensors are copied to the device first
+        (that copy is part of the end-to-end measurement in bench.py)."""
+        dev = self.device
+        noise = noise.to(dev, non_blocking=True)
+        c = {k: v.to(dev, non_blocking=True) for k, v in c.items()}
+        uc = {k: v.to(dev, non_blocking=True) for k, v in uc.items()}
+        z = self.sample_latents(noise, c, uc, num_steps)
+        frames = self.decode_first_stage(z) if decode else None
+        return z, frames
