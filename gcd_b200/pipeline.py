@@ -62,3 +62,26 @@ class GCDHotPath:
         z = self.sample_latents(noise, c, uc, num_steps)
         frames = self.decode_first_stage(z) if decode else None
         return z, frames
+
+
+def shard_clips(num_clips, rank, world):
+    """Clip indices owned by `rank`: strided like the reference's per-GPU worker buckets
+    (`examples[bucket_idx::num_buckets]`, scripts/test.py:1059-1084). Clips are independent (SURVEY.md §8(e))."""
+    return list(range(num_clips))[rank::world]
+
+
+def gather_clips(local, num_clips, rank, world, group=None):
+    """All-gathers per-rank clip tensors (each [T, ...], same shape) back into clip order. The ONLY collective on the
+    path (NCCL over NVLink on GPUs; gloo in the CPU tests). local: list of tensors for shard_clips(num_clips, rank, world)."""
+    import torch.distributed as dist
+    per = (num_clips + world - 1) // world
+    proto = local[0]
+    pad = [torch.zeros_like(proto) for _ in range(per - len(local))]
+    mine = torch.stack(list(local) + pad)                       # [per, T, ...]
+    bufs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine, group=group)
+    out = [None] * num_clips
+    for r in range(world):
+        for j, idx in enumerate(shard_clips(num_clips, r, world)):
+            out[idx] = bufs[r][j]
+    return out

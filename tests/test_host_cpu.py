@@ -1,0 +1,154 @@
+"""CPU tests: oracle pinned to the reference's golden vectors, host-side sampler classes, FLOP model, C-ABI exports,
+and the world_size-2 gloo path of the clip sharding/gather."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from gcd_b200 import flops, sampling, spec, synthetic  # noqa: E402
+from oracle import gcd_oracle as O  # noqa: E402
+
+
+def maxrel(a, b):
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+# ------------------------------------------------------------------------------------------- oracle vs reference goldens
+def test_closed_forms_bit_exact():
+    g = torch.load(os.path.join(GOLD, "closed_forms.pt"))
+    for n in (25, 50):
+        assert torch.equal(O.edm_sigmas(n), g[f"sigmas_{n}"])
+        assert torch.equal(sampling.EDMDiscretization(sigma_max=700.0)(n, device="cpu"), g[f"sigmas_{n}"])
+    assert abs(g["sigmas_25"][0].item() - 700.0001) < 1e-3 and g["sigmas_25"][-1].item() == 0.0
+    assert torch.equal(O.guider_scale(14, 1.5), g["scale_1.5"]) and torch.equal(O.guider_scale(14, 2.5), g["scale_2.5"])
+    assert torch.equal(sampling.LinearPredictionGuider(1.5, 14, 1.0).scale, g["scale_1.5"])
+    assert torch.equal(O.timestep_embedding(g["temb_t"], 320), g["temb_320"])
+
+
+def test_oracle_unet_and_sampler_vs_reference_golden():
+    gold = torch.load(os.path.join(GOLD, "unet_tiny.pt"))
+    cfg, B, T, H, W = gold["cfg"], gold["B"], gold["T"], gold["H"], gold["W"]
+    sd = synthetic.seeded_state(spec.unet_param_shapes(cfg), seed=0)
+    x, c, uc, ioi = synthetic.seeded_inputs(cfg, B, T, H, W)
+    net = lambda xin, t, ctx, y, **kw: O.unet_forward(sd, cfg, xin, t, ctx, y, kw["num_video_frames"], kw["image_only_indicator"])
+    extra = dict(image_only_indicator=ioi, num_video_frames=T)
+    c_cat = {k: torch.cat((uc[k], c[k]), 0) for k in c}
+    with torch.no_grad():
+        den = O.denoise(net, torch.cat([x, x]) * gold["x_mul"], torch.full((2 * B * T,), gold["sigma"]), c_cat, **extra)
+        samp = O.euler_edm_sample(net, x.clone(), c, uc, gold["steps"], T, 1.5, 1.0, **extra)
+    assert maxrel(den, gold["denoised"]) < 2e-5
+    assert maxrel(samp, gold["sampled"]) < 2e-4
+
+
+def test_oracle_decoder_vs_reference_golden():
+    gold = torch.load(os.path.join(GOLD, "vae_tiny.pt"))
+    cfg = gold["cfg"]
+    sd = synthetic.seeded_state(spec.decoder_param_shapes(cfg), seed=0)
+    g = torch.Generator().manual_seed(gold["z_seed"])
+    z = torch.randn(gold["T"], cfg["z_channels"], gold["H"], gold["W"], generator=g)
+    with torch.no_grad():
+        out = O.decode_first_stage(sd, cfg, z, gold["T"])
+    assert maxrel(out, gold["decoded"]) < 2e-5
+
+
+def test_len1_cross_attention_is_a_bias():
+    """with one context token attn2(x, ctx) == to_out(to_v(ctx)), independent of x."""
+    torch.manual_seed(0)
+    C, ctxd = 128, 1024
+    sd = {"a.to_q.weight": torch.randn(C, C), "a.to_k.weight": torch.randn(C, ctxd), "a.to_v.weight": torch.randn(C, ctxd),
+          "a.to_out.0.weight": torch.randn(C, C), "a.to_out.0.bias": torch.randn(C)}
+    x, ctx = torch.randn(3, 17, C), torch.randn(3, 1, ctxd)
+    full = O.attention(sd, "a", x, ctx, heads=2)
+    vec = torch.nn.functional.linear(torch.nn.functional.linear(ctx, sd["a.to_v.weight"]), sd["a.to_out.0.weight"], sd["a.to_out.0.bias"])
+    assert torch.allclose(full, vec.expand_as(full), atol=1e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- host-side sampler classes
+def test_generic_sampler_matches_oracle_with_fake_network():
+    T, B, H, W = 3, 2, 4, 4
+    torch.manual_seed(0)
+    x = torch.randn(B * T, 4, H, W)
+    c = {"vector": torch.randn(B * T, 8), "crossattn": torch.randn(B * T, 1, 16), "concat": torch.randn(B * T, 4, H, W)}
+    uc = {"vector": c["vector"].clone(), "crossattn": torch.zeros_like(c["crossattn"]), "concat": torch.zeros_like(c["concat"])}
+
+    class Net(torch.nn.Module):   # any network obeying the VideoUNet call contract
+        def forward(self, x, timesteps=None, context=None, y=None, **kw):
+            return torch.tanh(x[:, :4] * 0.5 + x[:, 4:] * 0.1 + timesteps.view(-1, 1, 1, 1) + context.mean() + y.mean())
+
+    net = Net()
+    den = sampling.Denoiser({"target": "gcd_b200.sampling.VScalingWithEDMcNoise"})
+    model = sampling.OpenAIWrapper(net)
+    sampler = sampling.EulerEDMSampler(
+        {"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization", "params": {"sigma_max": 700.0}},  # alias
+        num_steps=6, guider_config={"target": "gcd_b200.sampling.LinearPredictionGuider",
+                                    "params": {"num_frames": T, "max_scale": 2.5, "min_scale": 1.0}}, device="cpu")
+    out = sampler(lambda i, s, cc: den(model, i, s, cc, num_video_frames=T), x.clone(), cond=c, uc=uc)
+    assert sampler.last_path == "generic"
+    ref = O.euler_edm_sample(lambda xin, t, ctx, y, **kw: net(xin, timesteps=t, context=ctx, y=y), x.clone(), c, uc, 6, T, 2.5, 1.0)
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5)
+    # last Euler step lands exactly on the denoised sample (sigma_next = 0), sampling.py:86-87
+    assert sampler.discretization(6)[-1] == 0
+
+
+def test_unsupported_options_fail_loudly():
+    from gcd_b200.unet import VideoUNet
+    kw = spec.unet_ctor_kwargs(spec.UNET_TINY)
+    with pytest.raises(NotImplementedError):
+        VideoUNet(**dict(kw, num_head_channels=32))
+    with pytest.raises(NotImplementedError):
+        VideoUNet(**dict(kw, merge_strategy="fixed"))
+    net = VideoUNet(**kw)
+    with pytest.raises(RuntimeError):   # no CPU fallback
+        net(torch.zeros(2, 8, 8, 8), torch.zeros(2), context=torch.zeros(2, 1, 1024), y=torch.zeros(2, 896), num_video_frames=2)
+
+
+def test_flop_model_matches_survey():
+    u = flops.unet_forward_flops(spec.UNET_KUBRIC, 28, 72, 128)
+    v = flops.decoder_flops(spec.VAE_DECODER, 14, 72, 128)
+    assert abs(u / 1e12 - 86.160) < 0.01 and abs(v / 1e12 - 97.202) < 0.01
+    assert abs(flops.clip_flops(spec.UNET_KUBRIC, spec.VAE_DECODER, 14, 72, 128, 25) / 14e12 - 160.8) < 0.05
+
+
+# ------------------------------------------------------------------------------------------- C ABI
+def test_c_abi_exports_every_declared_symbol():
+    from gcd_b200 import _lib, build
+    build.build()                                  # cross-compiles for sm_100a; no GPU needed
+    hdr = open(os.path.join(ROOT, "include", "gcd_b200.h")).read()
+    declared = set(re.findall(r"\b(gcd_[a-z0-9_]+)\s*\(", hdr))
+    lib = _lib.load()
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.gcd_version() >= 100 and lib.gcd_act_dtype() in (0, 1)
+
+
+# ------------------------------------------------------------------------------------------- multi-process (gloo, 2 ranks)
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from gcd_b200.pipeline import gather_clips, shard_clips
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    num_clips = 5
+    mine = shard_clips(num_clips, rank, world)
+    local = [torch.full((14, 4, 2, 2), float(i)) for i in mine]
+    out = gather_clips(local, num_clips, rank, world)
+    ok = all(bool((out[i] == float(i)).all()) for i in range(num_clips))
+    q.put((rank, mine, ok))
+    dist.destroy_process_group()
+
+
+def test_clip_sharding_and_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3] and all(r[2] for r in res)
