@@ -229,9 +229,9 @@ extern "C" int gcd_attention_spatial(const void* qkv, int frames, int tokens, in
     uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)tokens, (uint64_t)frames};
     uint64_t str[2] = {(uint64_t)3 * C * 2, (uint64_t)tokens * 3 * C * 2};
     uint32_t boxq[3] = {64, fa::BQ, 1}, boxk[3] = {64, fa::BK, 1};
-    int rc = gcd_make_tmap(&mQ, qkv, 3, dims, str, boxq, nullptr, 1);
+    int rc = gcd_make_tmap(&mQ, qkv, 3, dims, str, boxq, nullptr, 128, 0);
     if (rc) return rc;
-    rc = gcd_make_tmap(&mKV, qkv, 3, dims, str, boxk, nullptr, 1);
+    rc = gcd_make_tmap(&mKV, qkv, 3, dims, str, boxk, nullptr, 128, 0);
     if (rc) return rc;
     fa::Params p;
     p.tokens = tokens; p.heads = heads; p.nblk = (tokens + fa::BK - 1) / fa::BK; p.out = (act_t*)out;

@@ -2,13 +2,17 @@
 //
 // One persistent, warp-specialised kernel per output-tile width BN in {128,160,256}:
 //   warp 0   : TMA producer  — per (tap, 64-channel chunk): one 4-D box of the channels-last activation tensor
-//              (out-of-range coordinates zero-filled by TMA = conv zero padding) + one 2-D/3-D box of the weights,
+//              (out-of-range coordinates zero-filled by TMA = conv zero padding) + one 3-D box of the weights,
 //              both landing 128B-swizzled in shared memory, signalled on an mbarrier ring.
 //   warp 1   : MMA issuer    — a single thread issues tcgen05.mma (M=128, N=BN, K=16, fp32 accumulate in TMEM),
 //              tcgen05.commit frees smem stages and publishes the accumulator.
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages so the epilogue overlaps the next tile's MMAs).
-//   warps 4-7: epilogue      — tcgen05.ld accumulator rows, fused bias / per-frame vector / activation / GEGLU /
-//              residual blend, vectorised global stores.
+//   warps 4-7: epilogue      — per 32-column chunk: tcgen05.ld the accumulator row of each thread, fused
+//              bias / per-frame vector / SiLU / GEGLU / residual blend, then a swizzled smem staging tile that one
+//              thread hands to the TMA store engine (cp.async.bulk.tensor ... bulk_group). Residual tiles are
+//              prefetched one chunk ahead by TMA loads into swizzled smem. No per-thread global loads/stores of
+//              activations, no bounds checks (TMA clips), compact code (the previous register-transposed epilogue was
+//              instruction-cache bound: profiles/r1_epilogue_icache.md).
 // Replaces cuDNN/cuBLAS calls behind nn.Conv2d / nn.Conv3d / nn.Linear in
 //   gcd-model/sgm/modules/diffusionmodules/openaimodel.py:213-357 (ResBlock), :110-210 (Up/Downsample),
 //   gcd-model/sgm/modules/attention.py:87-113,255-344 (FeedForward/GEGLU, CrossAttention projections),
@@ -32,7 +36,7 @@ void gcd_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 extern "C" const char* gcd_last_error(void) { return g_err; }
-extern "C" int gcd_version(void) { return 100; }
+extern "C" int gcd_version(void) { return 101; }
 extern "C" int gcd_act_dtype(void) { return (int)GCD_UMMA_FMT; }
 extern "C" int64_t gcd_launch_count(void) { return g_launches.load(); }
 
@@ -51,7 +55,7 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 int gcd_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, const uint32_t* elem_strides, int swizzle128) {
+                  const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes, int f32) {
     PFN_encodeTiled enc = get_encode();
     GCD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
     cuuint64_t d[5], s[4];
@@ -67,14 +71,17 @@ int gcd_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 #else
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 #endif
-    CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+    if (f32) dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GCD_REQUIRE(r == CUDA_SUCCESS,
-                "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u stride0 %llu", (int)r,
+                "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u stride0 %llu f32 %d", (int)r,
                 rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
                 (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0), b[0],
-                rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0, (unsigned long long)s[0]);
+                rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0, (unsigned long long)s[0], f32);
     return 0;
 }
 
@@ -88,159 +95,71 @@ struct TcParams {
     int8_t tdx[9], tdy[9], tdz[9];
     int N, n_tiles;
     int w_batched;
+    int stages;                 // smem ring depth (runtime: depends on which epilogue staging buffers are needed)
     // epilogue
     const float* bias;
     const float* rowvec;
     int rpv, ldv;
-    const void* r1;
-    const void* r2;
-    int ld1, ld2, r1f32, r2f32;
+    int has_r1, has_r2, r1f32, r2f32;
     float a0, a1, a2;
-    void* out;
-    int ldo, of32, geglu, act, vec_ok;
+    int of32, geglu, act;
 };
 
-template <int BN>
-struct TcCfg {
-    static constexpr int A_BYTES = 128 * 128;
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGES = (BN == 256) ? 4 : 5;
-    static constexpr int EPI_LD = 36;                       // floats per staged row (32 + 4 pad: conflict-free)
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // one 32x32 fp32 chunk per epilogue warp
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-};
+constexpr int TC_A_BYTES = 128 * 128;
+constexpr int TC_STG_BYTES = 128 * 128;       // one staging tile: 128 rows x <=128 B
+constexpr int TC_SMEM_MAX = 232448 - 2048;    // 227 KB minus alignment slack
 
-// ---- coalesced epilogue helpers: a lane owns 4 consecutive output columns of one row -------------------------
-__device__ __forceinline__ void load_res4(float* x, const void* R, int64_t off, bool f32, float a, int nv, bool vec) {
-    if (f32) {
-        const float* r = reinterpret_cast<const float*>(R) + off;
-        if (vec) {
-            float4 t = *reinterpret_cast<const float4*>(r);
-            x[0] += a * t.x; x[1] += a * t.y; x[2] += a * t.z; x[3] += a * t.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j < nv) x[j] += a * r[j];
-        }
-    } else {
-        const act_t* r = reinterpret_cast<const act_t*>(R) + off;
-        if (vec) {
-            uint2 t = *reinterpret_cast<const uint2*>(r);
-            float2 f0 = unpack2(t.x), f1 = unpack2(t.y);
-            x[0] += a * f0.x; x[1] += a * f0.y; x[2] += a * f1.x; x[3] += a * f1.y;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j < nv) x[j] += a * act2f(r[j]);
-        }
-    }
-}
-__device__ __forceinline__ void store4(void* out, int64_t off, bool f32, const float* x, int nv, bool vec) {
-    if (f32) {
-        float* o = reinterpret_cast<float*>(out) + off;
-        if (vec) *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j < nv) o[j] = x[j];
-        }
-    } else {
-        act_t* o = reinterpret_cast<act_t*>(out) + off;
-        if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack2(x[0], x[1]), pack2(x[2], x[3]));
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j < nv) o[j] = f2act(x[j]);
-        }
-    }
+__device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+
+// Row r of a swizzled staging tile whose rows are `nch` 16-byte chunks wide (8: SW128, 4: SW64, 2: SW32):
+// byte offset of logical chunk c  (Swizzle<B,4,3> with B = log2(nch); sh = 3 - B).
+__device__ __forceinline__ uint32_t stg_off(int r, int c, int nch, int sh) {
+    return (uint32_t)(r * nch + (c ^ ((r >> sh) & (nch - 1)))) << 4;
 }
 
-// One 32-accumulator-column chunk of one warp's 32 rows, read back from the staging tile in coalesced order.
-// LPR lanes cover one row (4 output columns per lane); LPR = 8 (plain) or 4 (GEGLU: 16 value + 16 gate columns).
-// Phase 1 issues every residual load of the chunk (memory-level parallelism), phase 2 computes and stores.
-template <int LPR>
-__device__ __forceinline__ void epi_chunk(const TcParams& p, const float* stg, int ld, int q, int lane, int nbase,
-                                          int tx, int ty, int tz, int TW, int TH, int TN) {
-    constexpr int RPS = 32 / LPR, STEPS = LPR;
-    constexpr bool GEGLU = (LPR == 4);
-    const int c4 = (lane % LPR) * 4;
-    const int rsub = lane / LPR;
-    const int Nout = GEGLU ? (p.N >> 1) : p.N;
-    const int n = nbase + c4;                                  // accumulator (value) column of this lane
-    const int ncol = GEGLU ? (nbase >> 1) + c4 : n;            // output column
-    const int nv = Nout - ncol;
-    if (nv <= 0) return;
-    const bool vec = p.vec_ok && nv >= 4;
-    float bv[4] = {0.f, 0.f, 0.f, 0.f}, bg[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.bias) {
+// x[0..32) += a * (row r of a swizzled residual tile holding 32 columns, float32 or act)
+__device__ __forceinline__ void add_residual_row(float* xf, const uint8_t* base, int r, bool f32, float a) {
+    if (f32) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (n + j < p.N) bv[j] = __ldg(p.bias + n + j);
-            if (GEGLU) bg[j] = __ldg(p.bias + n + 16 + j);
+        for (int c = 0; c < 8; c++) {
+            const uint4 t = ld_shared_v4(base + stg_off(r, c, 8, 0));
+            xf[4 * c] += a * __uint_as_float(t.x); xf[4 * c + 1] += a * __uint_as_float(t.y);
+            xf[4 * c + 2] += a * __uint_as_float(t.z); xf[4 * c + 3] += a * __uint_as_float(t.w);
         }
-    }
-    int64_t rows[STEPS];
-    float r1v[STEPS][4], r2v[STEPS][4];
+    } else {
 #pragma unroll
-    for (int s = 0; s < STEPS; s++) {
-        const int r = q * 32 + s * RPS + rsub;
-        const int x = tx * TW + (r & (TW - 1));
-        const int y = ty * TH + ((r >> p.lTW) & (TH - 1));
-        const int z = tz * TN + (r >> (p.lTW + p.lTH));
-        const bool valid = (x < p.Xo) && (y < p.Yo) && (z < p.Zo);
-        rows[s] = valid ? ((int64_t)z * p.Yo + y) * p.Xo + x : -1;
-#pragma unroll
-        for (int j = 0; j < 4; j++) { r1v[s][j] = 0.f; r2v[s][j] = 0.f; }
-        if (valid) {
-            if (p.r1) load_res4(r1v[s], p.r1, rows[s] * p.ld1 + ncol, p.r1f32, p.a1, nv, vec);
-            if (p.r2) load_res4(r2v[s], p.r2, rows[s] * p.ld2 + ncol, p.r2f32, p.a2, nv, vec);
+        for (int c = 0; c < 4; c++) {
+            const uint4 t = ld_shared_v4(base + stg_off(r, c, 4, 1));
+            float2 f;
+            f = unpack2(t.x); xf[8 * c] += a * f.x; xf[8 * c + 1] += a * f.y;
+            f = unpack2(t.y); xf[8 * c + 2] += a * f.x; xf[8 * c + 3] += a * f.y;
+            f = unpack2(t.z); xf[8 * c + 4] += a * f.x; xf[8 * c + 5] += a * f.y;
+            f = unpack2(t.w); xf[8 * c + 6] += a * f.x; xf[8 * c + 7] += a * f.y;
         }
-    }
-#pragma unroll
-    for (int s = 0; s < STEPS; s++) {
-        if (rows[s] < 0) continue;
-        const int rl = s * RPS + rsub;
-        float xf[4];
-        {
-            float4 t = *reinterpret_cast<const float4*>(stg + rl * ld + c4);
-            xf[0] = t.x + bv[0]; xf[1] = t.y + bv[1]; xf[2] = t.z + bv[2]; xf[3] = t.w + bv[3];
-        }
-        const float* rv = p.rowvec ? p.rowvec + (rows[s] / p.rpv) * (int64_t)p.ldv + n : nullptr;
-        if (rv) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (n + j < p.N) xf[j] += __ldg(rv + j);
-        }
-        if (GEGLU) {
-            float4 g = *reinterpret_cast<const float4*>(stg + rl * ld + 16 + c4);
-            float gg[4] = {g.x + bg[0], g.y + bg[1], g.z + bg[2], g.w + bg[3]};
-            if (rv) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) gg[j] += __ldg(rv + 16 + j);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) xf[j] *= gelu_erf(gg[j]);
-        }
-        if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) xf[j] = silu(xf[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) xf[j] = p.a0 * xf[j] + r1v[s][j] + r2v[s][j];
-        store4(p.out, rows[s] * p.ldo + ncol, p.of32, xf, nv, vec);
     }
 }
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
-    using Cfg = TcCfg<BN>;
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapR1,
+               const __grid_constant__ CUtensorMap mapR2, const TcParams p) {
+    constexpr int B_BYTES = BN * 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGES = p.stages;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-    float* sEpi = reinterpret_cast<float*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::EPI_BYTES);
-    uint64_t* full = bars;                       // [STAGES]
-    uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
-    uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]
-    uint64_t* tempty = tfull + 2;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint8_t* sB = sA + STAGES * TC_A_BYTES;
+    uint8_t* sO = sB + STAGES * B_BYTES;                    // [2] output staging
+    uint8_t* sR1 = sO + 2 * TC_STG_BYTES;                   // [2] residual 1 (if any)
+    uint8_t* sR2 = sR1 + (p.has_r1 ? 2 * TC_STG_BYTES : 0); // [2] residual 2 (if any)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (p.has_r2 ? 2 * TC_STG_BYTES : 0));
+    uint64_t* full = bars;                 // [STAGES]
+    uint64_t* empty = bars + 8;            // [STAGES]  (STAGES <= 8)
+    uint64_t* tfull = bars + 16;           // [2]
+    uint64_t* tempty = bars + 18;          // [2]
+    uint64_t* rfull = bars + 20;           // [2] residual tiles landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -248,15 +167,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
+        prefetch_tmap(&mapO);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < Cfg::STAGES; i++) {
+        for (int i = 0; i < STAGES; i++) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 128);
+            mbar_init(&rfull[i], 1);
         }
         fence_barrier_init();
     }
@@ -290,10 +211,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int cx = x0 + p.tdx[tap], cy = y0 + p.tdy[tap], cz = z0 + p.tdz[tap];
                     for (int kc = 0; kc < p.kchunks; kc++, kidx += 64) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-                        tma_load_4d(&mapA, sA + stage * Cfg::A_BYTES, &full[stage], kc * 64, cx, cy, cz);
-                        tma_load_3d(&mapB, sB + stage * Cfg::B_BYTES, &full[stage], kidx, nt * BN, wy);
-                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                        mbar_expect_tx(&full[stage], TC_A_BYTES + B_BYTES);
+                        tma_load_4d(&mapA, sA + stage * TC_A_BYTES, &full[stage], kc * 64, cx, cy, cz);
+                        tma_load_3d(&mapB, sB + stage * B_BYTES, &full[stage], kidx, nt * BN, wy);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -314,23 +235,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int ki = 0; ki < kiters; ki++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t ad = make_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES), 16, 1024);
-                    const uint64_t bd = make_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES), 16, 1024);
+                    const uint64_t ad = make_desc_sw128(smem_u32(sA + stage * TC_A_BYTES), 16, 1024);
+                    const uint64_t bd = make_desc_sw128(smem_u32(sB + stage * B_BYTES), 16, 1024);
 #pragma unroll
                     for (int k = 0; k < 4; k++)   // 4 x (K=16) inside the 64-wide swizzle atom: +32 B each
                         umma_f16_ss(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ki | k) != 0);
                     umma_commit(&empty[stage]);
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[as]);
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        // TMEM rows arrive one-per-thread; each 32-column chunk is transposed through a per-warp smem tile so that
-        // global loads/stores are coalesced: a lane then owns 4 consecutive columns, LPR lanes cover one row.
-        const int q = warp & 3;              // TMEM lane quadrant of this warp
-        float* stg = sEpi + q * 32 * Cfg::EPI_LD;
+        const int q = warp & 3;                     // TMEM lane quadrant of this warp
+        const int r = q * 32 + lane;                // tile row of this thread (= TMEM lane)
+        const bool leader = (threadIdx.x == 128);   // issues the epilogue's TMA loads / stores
+        const bool has_res = p.has_r1 || p.has_r2;
+        const uint32_t rbytes = (p.has_r1 ? (p.r1f32 ? 16384u : 8192u) : 0u) + (p.has_r2 ? (p.r2f32 ? 16384u : 8192u) : 0u);
+
+        // residual prefetcher (leader only): runs one chunk ahead of the consumer
+        int pf_tile = blockIdx.x, pf_c0 = 0;
+        uint32_t pf_i = 0;
+        auto prefetch_residual = [&]() {
+            if (pf_tile >= total) return;
+            const int nt = pf_tile % p.n_tiles, mt = pf_tile / p.n_tiles;
+            const int tx = mt % p.ntx, ty = (mt / p.ntx) % p.nty, tz = mt / (p.ntx * p.nty);
+            const int ncol = nt * BN + pf_c0;
+            const int b = pf_i & 1;
+            mbar_expect_tx(&rfull[b], rbytes);
+            if (p.has_r1) tma_load_4d(&mapR1, sR1 + b * TC_STG_BYTES, &rfull[b], ncol, tx * TW, ty * TH, tz * TN);
+            if (p.has_r2) tma_load_4d(&mapR2, sR2 + b * TC_STG_BYTES, &rfull[b], ncol, tx * TW, ty * TH, tz * TN);
+            pf_i++;
+            pf_c0 += 32;
+            if (pf_c0 >= BN || nt * BN + pf_c0 >= p.N) { pf_c0 = 0; pf_tile += gridDim.x; }
+        };
+        if (leader && has_res) prefetch_residual();
+
+        uint32_t ci = 0;                            // chunk counter of this CTA
         int it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
             const int as = it & 1;
@@ -341,31 +283,105 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int ty = (mt / p.ntx) % p.nty;
             const int tz = mt / (p.ntx * p.nty);
             const int n0 = nt * BN;
-
+            const float* rv = nullptr;
+            if (p.rowvec) {
+                const int x = tx * TW + (r & (TW - 1));
+                const int y = ty * TH + ((r >> p.lTW) & (TH - 1));
+                const int z = tz * TN + (r >> (p.lTW + p.lTH));
+                if (x < p.Xo && y < p.Yo && z < p.Zo)
+                    rv = p.rowvec + ((((int64_t)z * p.Yo + y) * p.Xo + x) / p.rpv) * (int64_t)p.ldv;
+            }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += 32, ci++) {
+                const int b = ci & 1;
+                if (leader) {
+                    if (has_res) prefetch_residual();        // chunk ci+1 -> buffer b^1 (released by barrier B2 of chunk ci-1)
+                    bulk_wait_read<1>();                     // the store of chunk ci-2 has finished reading sO[b]
+                }
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
-                if (n0 + c0 >= p.N) continue;     // warp-uniform
-                {
-                    float4* dst = reinterpret_cast<float4*>(stg + lane * Cfg::EPI_LD);
+                float xf[32];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                for (int j = 0; j < 32; j++) xf[j] = __uint_as_float(v[j]);
+                const int n = n0 + c0;
+                if (n + 32 <= p.N) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                            xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
+                        }
+                    }
+                    if (rv) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+                            xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
+                        }
+                    }
+                } else {                                      // ragged N tail (e.g. the 4-channel output conv)
+#pragma unroll 1
+                    for (int j = 0; j < p.N - n; j++) {
+                        const float add = (p.bias ? p.bias[n + j] : 0.f) + (rv ? rv[n + j] : 0.f);
+#pragma unroll
+                        for (int k = 0; k < 32; k++) if (k == j) xf[k] += add;
+                    }
                 }
-                __syncwarp();
-                if (p.geglu) epi_chunk<4>(p, stg, Cfg::EPI_LD, q, lane, n0 + c0, tx, ty, tz, TW, TH, TN);
-                else         epi_chunk<8>(p, stg, Cfg::EPI_LD, q, lane, n0 + c0, tx, ty, tz, TW, TH, TN);
-                __syncwarp();
+                if (p.geglu) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) xf[j] *= gelu_erf(xf[16 + j]);
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) xf[j] = silu(xf[j]);
+                }
+                if (p.a0 != 1.0f) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) xf[j] *= p.a0;
+                }
+                if (has_res) {
+                    mbar_wait(&rfull[b], (ci >> 1) & 1);
+                    if (p.has_r1) add_residual_row(xf, sR1 + b * TC_STG_BYTES, r, p.r1f32, p.a1);
+                    if (p.has_r2) add_residual_row(xf, sR2 + b * TC_STG_BYTES, r, p.r2f32, p.a2);
+                }
+                named_bar_sync(1, 128);                       // B1: sO[b] is free (leader waited on the bulk group)
+                {
+                    uint8_t* base = sO + b * TC_STG_BYTES;
+                    if (p.of32) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            *reinterpret_cast<uint4*>(base + stg_off(r, c, 8, 0)) =
+                                make_uint4(__float_as_uint(xf[4 * c]), __float_as_uint(xf[4 * c + 1]),
+                                           __float_as_uint(xf[4 * c + 2]), __float_as_uint(xf[4 * c + 3]));
+                    } else if (p.geglu) {                     // 16 output columns: 32-byte rows, SWIZZLE_32B
+#pragma unroll
+                        for (int c = 0; c < 2; c++)
+                            *reinterpret_cast<uint4*>(base + stg_off(r, c, 2, 2)) =
+                                make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
+                                           pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
+                    } else {                                  // 32 output columns: 64-byte rows, SWIZZLE_64B
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            *reinterpret_cast<uint4*>(base + stg_off(r, c, 4, 1)) =
+                                make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
+                                           pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);                       // B2: tile staged; residual buffer b fully consumed
+                if (leader) {
+                    tma_store_4d(&mapO, sO + b * TC_STG_BYTES, p.geglu ? (n >> 1) : n, tx * TW, ty * TH, tz * TN);
+                    bulk_commit();
+                }
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);
         }
+        if (leader) bulk_wait_read<0>();
     }
 
     tc_fence_before();
@@ -384,23 +400,42 @@ static int ilog2(int v) {
 }
 
 template <int BN>
-static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, cudaStream_t st) {
-    using Cfg = TcCfg<BN>;
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mR1,
+                     const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
     static bool configured = false;
     static int num_sms = 0;
+    constexpr int STAGE_BYTES = TC_A_BYTES + BN * 128;
     if (!configured) {
-        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX + 2048));
         int dev = 0;
         GCD_CUDA_CHECK(cudaGetDevice(&dev));
         GCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
+    const int epi = (2 + (p.has_r1 ? 2 : 0) + (p.has_r2 ? 2 : 0)) * TC_STG_BYTES;
+    int stages = (TC_SMEM_MAX - epi - 512) / STAGE_BYTES;
+    if (stages > 8) stages = 8;
+    GCD_REQUIRE(stages >= 2, "tc_gemm: not enough shared memory for the pipeline (BN=%d)", BN);
+    p.stages = stages;
+    const int smem = stages * STAGE_BYTES + epi + 512 + 1024;
     const int total = p.ntx * p.nty * p.ntz * p.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
-    tc_gemm_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(mA, mB, p);
+    tc_gemm_kernel<BN><<<grid, 256, smem, st>>>(mA, mB, mO, mR1, mR2, p);
     GCD_CUDA_CHECK(cudaGetLastError());
     g_launches++;
     return 0;
+}
+
+// 4-D map over an output-shaped tensor [Z, Y, X, cols] with leading dimension ld (elements), box = tile x `bcols`.
+static int make_out_map(CUtensorMap* m, const void* ptr, int f32, int ld, int cols, int Xo, int Yo, int Zo, int TW, int TH,
+                        int TN, int bcols, const char* what) {
+    const int es = f32 ? 4 : 2;
+    GCD_REQUIRE(((uintptr_t)ptr & 15) == 0 && ((int64_t)ld * es) % 16 == 0,
+                "gcd_tc_run: %s must be 16-byte aligned with a leading dimension multiple of 16 bytes (ld=%d)", what, ld);
+    uint64_t dims[4] = {(uint64_t)cols, (uint64_t)Xo, (uint64_t)Yo, (uint64_t)Zo};
+    uint64_t str[3] = {(uint64_t)ld * es, (uint64_t)ld * es * Xo, (uint64_t)ld * es * Xo * Yo};
+    uint32_t box[4] = {(uint32_t)bcols, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+    return gcd_make_tmap(m, ptr, 4, dims, str, box, nullptr, bcols * es, f32);
 }
 
 extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
@@ -413,8 +448,12 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     GCD_REQUIRE(((uintptr_t)op->A & 15) == 0 && ((uintptr_t)op->W & 15) == 0, "gcd_tc_run: operands must be 16B aligned");
     GCD_REQUIRE(op->in_mul == 1 || op->in_mul == 2, "gcd_tc_run: in_mul must be 1 or 2");
     const gcd_epilogue& e = op->ep;
-    GCD_REQUIRE(!e.geglu || (op->N % 32 == 0), "gcd_tc_run: GEGLU needs N %% 32 == 0");
+    GCD_REQUIRE(!e.geglu || (op->N % 32 == 0 && !e.out_f32 && !e.res1 && !e.res2),
+                "gcd_tc_run: GEGLU needs N %% 32 == 0, 16-bit output and no residual");
     GCD_REQUIRE(!e.rowvec || e.rows_per_vec > 0, "gcd_tc_run: rows_per_vec must be > 0");
+    GCD_REQUIRE(!e.bias || ((uintptr_t)e.bias & 15) == 0, "gcd_tc_run: bias must be 16B aligned");
+    GCD_REQUIRE(!e.rowvec || (((uintptr_t)e.rowvec & 15) == 0 && e.ld_rowvec % 4 == 0),
+                "gcd_tc_run: rowvec must be 16B aligned with ld %% 4 == 0");
 
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -456,50 +495,51 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     p.n_tiles = (op->N + BN - 1) / BN;
 
     p.bias = e.bias; p.rowvec = e.rowvec; p.rpv = e.rows_per_vec; p.ldv = e.ld_rowvec;
-    p.r1 = e.res1; p.r2 = e.res2; p.ld1 = e.ld_res1; p.ld2 = e.ld_res2; p.r1f32 = e.res1_f32; p.r2f32 = e.res2_f32;
+    p.has_r1 = e.res1 != nullptr; p.has_r2 = e.res2 != nullptr; p.r1f32 = e.res1_f32; p.r2f32 = e.res2_f32;
     p.a0 = e.a_acc; p.a1 = e.a_res1; p.a2 = e.a_res2;
-    p.out = e.out; p.ldo = e.ld_out; p.of32 = e.out_f32; p.geglu = e.geglu; p.act = e.act;
-    // vector path: 16-column runs must be 16B aligned for every tensor touched
-    auto ok = [](const void* ptr, int ld, int f32) {
-        if (!ptr) return true;
-        int a = f32 ? 4 : 8;
-        return (ld % a == 0) && (((uintptr_t)ptr & 15) == 0);
-    };
-    p.vec_ok = ok(e.out, e.ld_out, e.out_f32) && ok(e.res1, e.ld_res1, e.res1_f32) && ok(e.res2, e.ld_res2, e.res2_f32) &&
-               (!e.bias || ((uintptr_t)e.bias & 15) == 0);
+    p.of32 = e.out_f32; p.geglu = e.geglu; p.act = e.act;
 
     // ---- tensor maps
-    CUtensorMap mA, mB;
+    CUtensorMap mA, mB, mO, mR1, mR2;
     {
         uint64_t dims[4] = {(uint64_t)op->C, (uint64_t)op->Xi, (uint64_t)op->Yi, (uint64_t)op->Zi};
         uint64_t str[3] = {(uint64_t)op->sx * 2, (uint64_t)op->sy * 2, (uint64_t)op->sz * 2};
-        uint32_t box[4] = {64, (uint32_t)(TW * op->in_mul), (uint32_t)(TH * op->in_mul), (uint32_t)TN};
-        uint32_t es[4] = {1, (uint32_t)op->in_mul, (uint32_t)op->in_mul, 1};
-        if (op->in_mul == 2) {   // box spans 2*T-1 source elements -> exactly T samples
-            box[1] = 2 * TW - 1 > 0 ? 2 * TW - 1 : 1;
-            box[2] = 2 * TH - 1 > 0 ? 2 * TH - 1 : 1;
-            if (TW == 1) es[1] = 1;
-            if (TH == 1) es[2] = 1;
+        uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+        uint32_t es[4] = {1, 1, 1, 1};
+        if (op->in_mul == 2) {   // box spans 2*T-1 source elements traversed with stride 2 -> exactly T samples
+            if (TW > 1) { box[1] = 2 * TW - 1; es[1] = 2; }
+            if (TH > 1) { box[2] = 2 * TH - 1; es[2] = 2; }
         }
-        // degenerate extents: TMA needs stride > 0 & multiple of 16B even when extent is 1
         for (int i = 0; i < 3; i++) if (str[i] == 0) str[i] = 16;
-        int rc = gcd_make_tmap(&mA, op->A, 4, dims, str, box, es, 1);
+        int rc = gcd_make_tmap(&mA, op->A, 4, dims, str, box, es, 128, 0);
         if (rc) return rc;
     }
     {
         uint64_t nb = p.w_batched ? (uint64_t)op->Yo : 1;
-        uint64_t dims[3] = {(uint64_t)op->ntaps * (uint64_t)(p.kchunks * 64), (uint64_t)op->N, nb};
-        // K extent: the weight matrix must really have ntaps*kchunks*64 columns unless C%64==0 holds (host packs it so)
-        dims[0] = (uint64_t)op->ntaps * (uint64_t)op->C;
         GCD_REQUIRE(op->C % 64 == 0 || op->ntaps == 1, "gcd_tc_run: multi-tap ops need C %% 64 == 0 (got %d)", op->C);
+        uint64_t dims[3] = {(uint64_t)op->ntaps * (uint64_t)op->C, (uint64_t)op->N, nb};
         uint64_t str[2] = {(uint64_t)op->ldw * 2, (uint64_t)(p.w_batched ? op->w_batch_stride : op->ldw * (int64_t)op->N) * 2};
         uint32_t box[3] = {64, (uint32_t)BN, 1};
-        int rc = gcd_make_tmap(&mB, op->W, 3, dims, str, box, nullptr, 1);
+        int rc = gcd_make_tmap(&mB, op->W, 3, dims, str, box, nullptr, 128, 0);
         if (rc) return rc;
     }
+    {
+        const int Nout = e.geglu ? op->N / 2 : op->N;
+        int rc = make_out_map(&mO, e.out, e.out_f32, e.ld_out, Nout, op->Xo, op->Yo, op->Zo, TW, TH, TN, e.geglu ? 16 : 32, "out");
+        if (rc) return rc;
+        mR1 = mO; mR2 = mO;
+        if (e.res1) {
+            rc = make_out_map(&mR1, e.res1, e.res1_f32, e.ld_res1, op->N, op->Xo, op->Yo, op->Zo, TW, TH, TN, 32, "res1");
+            if (rc) return rc;
+        }
+        if (e.res2) {
+            rc = make_out_map(&mR2, e.res2, e.res2_f32, e.ld_res2, op->N, op->Xo, op->Yo, op->Zo, TW, TH, TN, 32, "res2");
+            if (rc) return rc;
+        }
+    }
     switch (BN) {
-        case 256: return launch_tc<256>(mA, mB, p, st);
-        case 160: return launch_tc<160>(mA, mB, p, st);
-        default: return launch_tc<128>(mA, mB, p, st);
+        case 256: return launch_tc<256>(mA, mB, mO, mR1, mR2, p, st);
+        case 160: return launch_tc<160>(mA, mB, mO, mR1, mR2, p, st);
+        default: return launch_tc<128>(mA, mB, mO, mR1, mR2, p, st);
     }
 }

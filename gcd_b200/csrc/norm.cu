@@ -206,11 +206,105 @@ __global__ void layernorm_kernel(const float* __restrict__ in, int64_t rows, int
     }
 }
 
+// Specialised version: NK float2 per lane per row, ROWS rows per warp in flight (4x the memory-level parallelism of the
+// generic kernel, which measured 0.96 TB/s at C=320 — latency bound; profiles/r1_notes.md).
+template <int NK, int ROWS>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ in, int64_t rows, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, const float* __restrict__ add, int64_t add_rows_per,
+                      int64_t add_mod, float* __restrict__ sum_out, act_t* __restrict__ out) {
+    constexpr int C = NK * 64;
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+    if (row0 >= rows) return;
+    float2 v[ROWS][NK];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        const int64_t row = row0 + r;
+        if (row < rows) {
+            const float2* src = reinterpret_cast<const float2*>(in + row * C);
+#pragma unroll
+            for (int k = 0; k < NK; k++) v[r][k] = src[lane + 32 * k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NK; k++) v[r][k] = make_float2(0.f, 0.f);
+        }
+    }
+    if (add) {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const int64_t row = row0 + r;
+            if (row < rows) {
+                const float2* ad = reinterpret_cast<const float2*>(add + ((row / add_rows_per) % add_mod) * C);
+#pragma unroll
+                for (int k = 0; k < NK; k++) { float2 a = __ldg(&ad[lane + 32 * k]); v[r][k].x += a.x; v[r][k].y += a.y; }
+                if (sum_out) {
+                    float2* so = reinterpret_cast<float2*>(sum_out + row * C);
+#pragma unroll
+                    for (int k = 0; k < NK; k++) so[lane + 32 * k] = v[r][k];
+                }
+            }
+        }
+    }
+    float g[NK * 2], b[NK * 2];
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(gamma) + lane + 32 * k);
+        g[2 * k] = t.x; g[2 * k + 1] = t.y;
+        t = __ldg(reinterpret_cast<const float2*>(beta) + lane + 32 * k);
+        b[2 * k] = t.x; b[2 * k + 1] = t.y;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NK; k++) s += v[r][k].x + v[r][k].y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            const float dx = v[r][k].x - mean, dy = v[r][k].y - mean;
+            q += dx * dx + dy * dy;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / C) + eps);
+        const int64_t row = row0 + r;
+        if (row < rows) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out + row * C);
+#pragma unroll
+            for (int k = 0; k < NK; k++)
+                dst[lane + 32 * k] = pack2((v[r][k].x - mean) * rstd * g[2 * k] + b[2 * k],
+                                           (v[r][k].y - mean) * rstd * g[2 * k + 1] + b[2 * k + 1]);
+        }
+    }
+}
+
+template <int NK, int ROWS>
+static int launch_ln(const float* in, int64_t rows, const float* gamma, const float* beta, float eps, const float* add,
+                     int64_t arp, int64_t amod, float* sum_out, void* out, void* stream) {
+    const int warps = 8;
+    const int64_t blocks = (rows + warps * ROWS - 1) / (warps * ROWS);
+    layernorm_rows_kernel<NK, ROWS><<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(
+        in, rows, gamma, beta, eps, add, arp, amod, sum_out, (act_t*)out);
+    GCD_CUDA_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
 extern "C" int gcd_layernorm(const float* in, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                              const float* add, int64_t add_rows_per, int64_t add_mod, float* sum_out, void* out,
                              void* stream) {
     GCD_REQUIRE(C % 64 == 0 && C <= 64 * LN_MAXK, "layernorm: C=%d must be a multiple of 64 and <= %d", C, 64 * LN_MAXK);
     GCD_REQUIRE(!add || (add_rows_per > 0 && add_mod > 0), "layernorm: bad add indexing");
+    switch (C) {
+        case 320: return launch_ln<5, 4>(in, rows, gamma, beta, eps, add, add_rows_per, add_mod, sum_out, out, stream);
+        case 640: return launch_ln<10, 4>(in, rows, gamma, beta, eps, add, add_rows_per, add_mod, sum_out, out, stream);
+        case 1280: return launch_ln<20, 2>(in, rows, gamma, beta, eps, add, add_rows_per, add_mod, sum_out, out, stream);
+        default: break;
+    }
     const int warps = 8;
     int64_t blocks = (rows + warps - 1) / warps;
     layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(in, rows, C, gamma, beta, eps, add,
