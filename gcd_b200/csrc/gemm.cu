@@ -7,7 +7,7 @@
 //   warp 1   : MMA issuer    — a single thread issues tcgen05.mma (M=128, N=BN, K=16, fp32 accumulate in TMEM),
 //              tcgen05.commit frees smem stages and publishes the accumulator.
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages so the epilogue overlaps the next tile's MMAs).
-//   warps 4-7: epilogue      — per 32-column chunk: tcgen05.ld the accumulator row of each thread, fused
+//   warps 4-11: epilogue     — two warpgroups alternating 32-column chunks; per chunk: tcgen05.ld the accumulator row of each thread, fused
 //              bias / per-frame vector / SiLU / GEGLU / residual blend, then a swizzled smem staging tile that one
 //              thread hands to the TMA store engine (cp.async.bulk.tensor ... bulk_group). Residual tiles are
 //              prefetched one chunk ahead by TMA loads into swizzled smem. No per-thread global loads/stores of
@@ -96,6 +96,7 @@ struct TcParams {
     int N, n_tiles;
     int w_batched;
     int stages;                 // smem ring depth (runtime: depends on which epilogue staging buffers are needed)
+    int obufs;                  // output staging tiles per epilogue warpgroup (2 when the K loop is short)
     // epilogue
     const float* bias;
     const float* rowvec;
@@ -140,7 +141,7 @@ __device__ __forceinline__ void add_residual_row(float* xf, const uint8_t* base,
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapR1,
                const __grid_constant__ CUtensorMap mapR2, const TcParams p) {
@@ -150,10 +151,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int STAGES = p.stages;
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * TC_A_BYTES;
-    uint8_t* sO = sB + STAGES * B_BYTES;                    // [2] output staging
-    uint8_t* sR1 = sO + 2 * TC_STG_BYTES;                   // [2] residual 1 (if any)
-    uint8_t* sR2 = sR1 + (p.has_r1 ? 2 * TC_STG_BYTES : 0); // [2] residual 2 (if any)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (p.has_r2 ? 2 * TC_STG_BYTES : 0));
+    const int OT = p.geglu ? 4096 : (p.of32 ? 16384 : 8192);          // bytes of one output staging tile
+    const int RT1 = p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0, RT2 = p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0;
+    uint8_t* sO = sB + STAGES * B_BYTES;                    // [2 warpgroups][obufs] output staging
+    uint8_t* sR1 = sO + 2 * p.obufs * OT;                   // [2] residual 1 (if any)
+    uint8_t* sR2 = sR1 + 2 * RT1;                           // [2] residual 2 (if any)
+    float* sBias = reinterpret_cast<float*>(sR2 + 2 * RT2); // [2][256] bias slice of the current tile, per warpgroup
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 512);
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + 8;            // [STAGES]  (STAGES <= 8)
     uint64_t* tfull = bars + 16;           // [2]
@@ -176,7 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&tempty[i], 256);
             mbar_init(&rfull[i], 1);
         }
         fence_barrier_init();
@@ -247,32 +251,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
+        // ===================== epilogue: two warpgroups, alternating 32-column chunks =====================
+        const int g = (warp - 4) >> 2;              // epilogue warpgroup 0 / 1 (own staging buffers, own named barrier)
         const int q = warp & 3;                     // TMEM lane quadrant of this warp
         const int r = q * 32 + lane;                // tile row of this thread (= TMEM lane)
-        const bool leader = (threadIdx.x == 128);   // issues the epilogue's TMA loads / stores
+        const bool leader = ((threadIdx.x & 127) == 0);   // issues this warpgroup's TMA loads / stores
         const bool has_res = p.has_r1 || p.has_r2;
         const uint32_t rbytes = (p.has_r1 ? (p.r1f32 ? 16384u : 8192u) : 0u) + (p.has_r2 ? (p.r2f32 ? 16384u : 8192u) : 0u);
+        uint8_t* myObase = sO + g * p.obufs * OT;
+        uint8_t* myR1 = sR1 + g * RT1;
+        uint8_t* myR2 = sR2 + g * RT2;
+        float* myBias = sBias + g * 256;
+        const int bar_id = 1 + g;
 
-        // residual prefetcher (leader only): runs one chunk ahead of the consumer
-        int pf_tile = blockIdx.x, pf_c0 = 0;
-        uint32_t pf_i = 0;
+        // residual prefetcher (leader only): the warpgroup's next chunk, issued as soon as its buffer is consumed
+        int pf_tile = blockIdx.x, pf_c0 = g * 32;
         auto prefetch_residual = [&]() {
+            while (pf_tile < total) {                                  // skip tiles where this warpgroup has no chunk
+                const int nt = pf_tile % p.n_tiles;
+                if (pf_c0 < BN && nt * BN + pf_c0 < p.N) break;
+                pf_c0 = g * 32; pf_tile += gridDim.x;
+            }
             if (pf_tile >= total) return;
             const int nt = pf_tile % p.n_tiles, mt = pf_tile / p.n_tiles;
             const int tx = mt % p.ntx, ty = (mt / p.ntx) % p.nty, tz = mt / (p.ntx * p.nty);
             const int ncol = nt * BN + pf_c0;
-            const int b = pf_i & 1;
-            mbar_expect_tx(&rfull[b], rbytes);
-            if (p.has_r1) tma_load_4d(&mapR1, sR1 + b * TC_STG_BYTES, &rfull[b], ncol, tx * TW, ty * TH, tz * TN);
-            if (p.has_r2) tma_load_4d(&mapR2, sR2 + b * TC_STG_BYTES, &rfull[b], ncol, tx * TW, ty * TH, tz * TN);
-            pf_i++;
-            pf_c0 += 32;
-            if (pf_c0 >= BN || nt * BN + pf_c0 >= p.N) { pf_c0 = 0; pf_tile += gridDim.x; }
+            mbar_expect_tx(&rfull[g], rbytes);
+            if (p.has_r1) tma_load_4d(&mapR1, myR1, &rfull[g], ncol, tx * TW, ty * TH, tz * TN);
+            if (p.has_r2) tma_load_4d(&mapR2, myR2, &rfull[g], ncol, tx * TW, ty * TH, tz * TN);
+            pf_c0 += 64;
         };
         if (leader && has_res) prefetch_residual();
 
-        uint32_t ci = 0;                            // chunk counter of this CTA
+        uint32_t ci = 0;                            // chunks processed by this warpgroup
         int it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
             const int as = it & 1;
@@ -291,16 +302,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (x < p.Xo && y < p.Yo && z < p.Zo)
                     rv = p.rowvec + ((((int64_t)z * p.Yo + y) * p.Xo + x) / p.rpv) * (int64_t)p.ldv;
             }
+            for (int j = threadIdx.x & 127; j < BN; j += 128)
+                myBias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            named_bar_sync(bar_id, 128);                      // B0: bias slice staged (also orders it after the previous tile's reads)
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += 32, ci++) {
-                const int b = ci & 1;
-                if (leader) {
-                    if (has_res) prefetch_residual();        // chunk ci+1 -> buffer b^1 (released by barrier B2 of chunk ci-1)
-                    bulk_wait_read<1>();                     // the store of chunk ci-2 has finished reading sO[b]
-                }
+            for (int c0 = g * 32; c0 < BN && n0 + c0 < p.N; c0 += 64, ci++) {
+                uint8_t* myO = myObase + (p.obufs == 2 ? (ci & 1) * OT : 0);
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
@@ -308,27 +318,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; j++) xf[j] = __uint_as_float(v[j]);
                 const int n = n0 + c0;
-                if (n + 32 <= p.N) {
-                    if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                            xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
-                        }
-                    }
-                    if (rv) {
+                for (int j = 0; j < 32; j += 4) {             // bias slice from smem (warp-broadcast reads)
+                    const float4 t = *reinterpret_cast<const float4*>(myBias + c0 + j);
+                    xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
+                }
+                if (rv) {
+                    if (n + 32 <= p.N) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n + j));
                             xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
                         }
-                    }
-                } else {                                      // ragged N tail (e.g. the 4-channel output conv)
+                    } else {                                  // ragged N tail
 #pragma unroll 1
-                    for (int j = 0; j < p.N - n; j++) {
-                        const float add = (p.bias ? p.bias[n + j] : 0.f) + (rv ? rv[n + j] : 0.f);
+                        for (int j = 0; j < p.N - n; j++) {
+                            const float add = rv[n + j];
 #pragma unroll
-                        for (int k = 0; k < 32; k++) if (k == j) xf[k] += add;
+                            for (int k = 0; k < 32; k++) if (k == j) xf[k] += add;
+                        }
                     }
                 }
                 if (p.geglu) {
@@ -344,38 +352,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int j = 0; j < 32; j++) xf[j] *= p.a0;
                 }
                 if (has_res) {
-                    mbar_wait(&rfull[b], (ci >> 1) & 1);
-                    if (p.has_r1) add_residual_row(xf, sR1 + b * TC_STG_BYTES, r, p.r1f32, p.a1);
-                    if (p.has_r2) add_residual_row(xf, sR2 + b * TC_STG_BYTES, r, p.r2f32, p.a2);
+                    mbar_wait(&rfull[g], ci & 1);
+                    if (p.has_r1) add_residual_row(xf, myR1, r, p.r1f32, p.a1);
+                    if (p.has_r2) add_residual_row(xf, myR2, r, p.r2f32, p.a2);
                 }
-                named_bar_sync(1, 128);                       // B1: sO[b] is free (leader waited on the bulk group)
-                {
-                    uint8_t* base = sO + b * TC_STG_BYTES;
-                    if (p.of32) {
+                if (leader) {                                 // the store that last used myO has drained it
+                    if (p.obufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                }
+                named_bar_sync(bar_id, 128);                  // B1: myO is free
+                if (p.of32) {
 #pragma unroll
-                        for (int c = 0; c < 8; c++)
-                            *reinterpret_cast<uint4*>(base + stg_off(r, c, 8, 0)) =
-                                make_uint4(__float_as_uint(xf[4 * c]), __float_as_uint(xf[4 * c + 1]),
-                                           __float_as_uint(xf[4 * c + 2]), __float_as_uint(xf[4 * c + 3]));
-                    } else if (p.geglu) {                     // 16 output columns: 32-byte rows, SWIZZLE_32B
+                    for (int c = 0; c < 8; c++)
+                        *reinterpret_cast<uint4*>(myO + stg_off(r, c, 8, 0)) =
+                            make_uint4(__float_as_uint(xf[4 * c]), __float_as_uint(xf[4 * c + 1]),
+                                       __float_as_uint(xf[4 * c + 2]), __float_as_uint(xf[4 * c + 3]));
+                } else if (p.geglu) {                         // 16 output columns: 32-byte rows, SWIZZLE_32B
 #pragma unroll
-                        for (int c = 0; c < 2; c++)
-                            *reinterpret_cast<uint4*>(base + stg_off(r, c, 2, 2)) =
-                                make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
-                                           pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
-                    } else {                                  // 32 output columns: 64-byte rows, SWIZZLE_64B
+                    for (int c = 0; c < 2; c++)
+                        *reinterpret_cast<uint4*>(myO + stg_off(r, c, 2, 2)) =
+                            make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
+                                       pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
+                } else {                                      // 32 output columns: 64-byte rows, SWIZZLE_64B
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            *reinterpret_cast<uint4*>(base + stg_off(r, c, 4, 1)) =
-                                make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
-                                           pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
-                    }
+                    for (int c = 0; c < 4; c++)
+                        *reinterpret_cast<uint4*>(myO + stg_off(r, c, 4, 1)) =
+                            make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
+                                       pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);                       // B2: tile staged; residual buffer b fully consumed
+                named_bar_sync(bar_id, 128);                  // B2: tile staged; residual buffer fully consumed
                 if (leader) {
-                    tma_store_4d(&mapO, sO + b * TC_STG_BYTES, p.geglu ? (n >> 1) : n, tx * TW, ty * TH, tz * TN);
+                    tma_store_4d(&mapO, myO, p.geglu ? (n >> 1) : n, tx * TW, ty * TH, tz * TN);
                     bulk_commit();
+                    if (has_res) prefetch_residual();         // next chunk of this warpgroup
                 }
             }
             tc_fence_before();
@@ -412,7 +421,12 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
         GCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
-    const int epi = (2 + (p.has_r1 ? 2 : 0) + (p.has_r2 ? 2 : 0)) * TC_STG_BYTES;
+    const int OT = p.geglu ? 4096 : (p.of32 ? 16384 : 8192);
+    const int RT = (p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0) + (p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0);
+    const int kiters = p.ntaps * p.kchunks;
+    // short K loop => the epilogue is the critical path: double-buffer its staging tiles if >= 3 pipeline stages remain
+    p.obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * RT) - 2560) / STAGE_BYTES >= 3) ? 2 : 1;
+    const int epi = 2 * p.obufs * OT + 2 * RT + 2048 /*bias*/;
     int stages = (TC_SMEM_MAX - epi - 512) / STAGE_BYTES;
     if (stages > 8) stages = 8;
     GCD_REQUIRE(stages >= 2, "tc_gemm: not enough shared memory for the pipeline (BN=%d)", BN);
@@ -420,7 +434,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     const int smem = stages * STAGE_BYTES + epi + 512 + 1024;
     const int total = p.ntx * p.nty * p.ntz * p.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
-    tc_gemm_kernel<BN><<<grid, 256, smem, st>>>(mA, mB, mO, mR1, mR2, p);
+    tc_gemm_kernel<BN><<<grid, 384, smem, st>>>(mA, mB, mO, mR1, mR2, p);
     GCD_CUDA_CHECK(cudaGetLastError());
     g_launches++;
     return 0;

@@ -25,6 +25,7 @@ def act_dtype():
 
 # ---- optional per-kernel-class timing (CUDA events on the launching stream); used by bench.py for `roofline` ----
 _PROF = None
+DETAIL = False   # per-shape names for tc_gemm launches while profiling (tools/prof_forward.py)
 
 
 class profile:
@@ -134,7 +135,10 @@ def tc_run(A, C, in_ext, in_strides, out_ext, taps, W, ldw, N, ep, in_mul=1, gem
     op.gemm_tile = int(bool(gemm_tile))
     op.W, op.ldw, op.w_batch_stride, op.N = W.data_ptr(), int(ldw), int(w_batch_stride), int(N)
     op.ep = ep
-    with _timed("tc_gemm", 2.0 * op.Xo * op.Yo * op.Zo * op.N * op.ntaps * op.C):
+    name = "tc_gemm"
+    if _PROF is not None and DETAIL:
+        name = f"tc M{op.Xo * op.Yo * op.Zo} N{op.N} K{op.ntaps * op.C} taps{op.ntaps} g{ep.geglu} r{int(bool(ep.res1))}{int(bool(ep.res2))} o{ep.out_f32}"
+    with _timed(name, 2.0 * op.Xo * op.Yo * op.Zo * op.N * op.ntaps * op.C):
         check(lib().gcd_tc_run(ctypes.byref(op), _stream()), "gcd_tc_run")
 
 
