@@ -168,7 +168,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
     unet_cfg, vae_cfg = getattr(spec, wl["unet"]), spec.VAE_DECODER
@@ -186,10 +187,10 @@ def main():
     d2h = frames_host.numel() * 4
     gathered = [torch.empty(T_FRAMES, 4, LAT_H, LAT_W, device=dev) for _ in range(world)] if world > 1 else None
 
-    def step_resident():
+    def step_resident(collective=True):
         z = pipe.sample_latents(dx.clone(), dc, duc)
         fr = None if args.no_decode else pipe.decode_first_stage(z)
-        if world > 1:
+        if world > 1 and collective:
             dist.all_gather(gathered, z.contiguous())     # the path's only collective: final gather over NVLink
         return z, fr
 
@@ -239,7 +240,7 @@ def main():
     if rank == 0:
         pk = measured_peaks()
         with ops.profile() as prof:
-            step_resident()
+            step_resident(collective=False)       # rank 0 only: must not enter a collective
         summ = prof.summary()
         tc = summ.get("tc_gemm", dict(ms=1e-9, flops=0.0, launches=0))
         tot_ms = sum(d["ms"] for d in summ.values())

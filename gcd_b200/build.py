@@ -30,9 +30,10 @@ def build(force=False, bf16=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         cmd = [nvcc, "-c", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-               "-std=c++17", "--use_fast_math" if False else "-DGCD_NO_FASTMATH", "-o", obj, os.path.join(CSRC, src)]
+               "-std=c++17", "-o", obj, os.path.join(CSRC, src)]
         if bf16:
             cmd.insert(1, "-DGCD_ACT_BF16")
+        cmd[1:1] = os.environ.get("GCD_NVCC_FLAGS", "").split()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

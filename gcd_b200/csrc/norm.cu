@@ -23,6 +23,7 @@ __global__ void gn_stats_kernel(const void* __restrict__ in, int64_t rows, int C
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(rows, r0 + rows_per_block);
     float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll 4
     for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
         const int64_t off = ((int64_t)img * rows + r) * C + c;
         float x0, x1, x2, x3;
@@ -73,6 +74,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ in, int64_t rows, int C
     const float4 b = *reinterpret_cast<const float4*>(beta + c);
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(rows, r0 + rows_per_block);
+#pragma unroll 4
     for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
         const int64_t off = ((int64_t)img * rows + r) * C + c;
         float x0, x1, x2, x3;
