@@ -123,10 +123,13 @@ def run_reference(args, wl):
     if rank != 0:
         return
     from gcd_b200 import spec
+    from gcd_b200 import synthetic
     unet_cfg, vae_cfg = getattr(spec, wl["unet"]), spec.VAE_DECODER
+    ust = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
+    vst = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
     vals = []
     for i in range(args.warmup + args.steps):
-        v, desc, cores, secs = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], sample_hw=(8, 16), vae_hw=(8, 8))
+        v, desc, cores, secs = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], ust, vst, sample_hw=(8, 16), vae_hw=(8, 8))
         if i >= args.warmup:
             vals.append((v, secs))
     v = sum(x[0] for x in vals) / len(vals)
