@@ -22,6 +22,7 @@ class Epilogue(Structure):
         ("res2", c_void_p), ("ld_res2", c_int32), ("res2_f32", c_int32),
         ("a_acc", c_float), ("a_res1", c_float), ("a_res2", c_float),
         ("out", c_void_p), ("ld_out", c_int32), ("out_f32", c_int32), ("geglu", c_int32), ("act", c_int32),
+        ("gn_stats", c_void_p), ("gn_cpg", c_int32), ("gn_groups", c_int32), ("gn_rows_per_img", c_int64),
     ]
 
 

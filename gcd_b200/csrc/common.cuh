@@ -199,22 +199,45 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
-// exact-erf GELU (torch F.gelu default). erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level for
-// the 16-bit result) with MUFU rcp/ex2: ~15 instructions instead of erff's ~30 — the GEGLU epilogue is ALU-bound.
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float ax = fabsf(x) * 0.70710678118654752f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
-    const float erf_abs = fmaf(-poly, e, 1.0f);
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2) ------------------------------------------------------
+__device__ __forceinline__ uint64_t pk2f(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
 }
+__device__ __forceinline__ void upk2f(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2f(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// GEGLU gate for a pair: returns (v0 * gelu(g0), v1 * gelu(g1)) with gelu(g) = g * Phi(g) (torch F.gelu, erf form).
+// Phi(g) - 1/2 = g * Q(g^2) on |g| <= 4 with a degree-7 minimax polynomial Q (max abs error of Phi 2.3e-5, tail beyond
+// |g| = 4 clamped: 3.2e-5) — no MUFU, 7 FFMA2 per pair. The previous erff / rcp+ex2 forms made the K=320 GEGLU GEMMs
+// MUFU- and issue-bound (profiles/r1_notes.md). Absolute error of the result <= 1.3e-4 * |v|, below the 16-bit
+// rounding of the output for the activation ranges of the network.
+__device__ __forceinline__ uint64_t geglu_pair(uint64_t v, float g0, float g1) {
+    const float l0 = fmaxf(g0, -4.0f), l1 = fmaxf(g1, -4.0f);        // multiplier: max(g, -4) bounds the far-tail error
+    const uint64_t gl = pk2f(l0, l1);
+    const uint64_t gc = pk2f(fminf(l0, 4.0f), fminf(l1, 4.0f));
+    const uint64_t u = mul2f(gc, gc);
+    uint64_t q = fma2f(u, pk2f(-1.5810971e-9f, -1.5810971e-9f), pk2f(1.2172849e-7f, 1.2172849e-7f));
+    q = fma2f(q, u, pk2f(-4.1012522e-6f, -4.1012522e-6f));
+    q = fma2f(q, u, pk2f(8.0671714e-5f, 8.0671714e-5f));
+    q = fma2f(q, u, pk2f(-1.0482300e-3f, -1.0482300e-3f));
+    q = fma2f(q, u, pk2f(9.6649509e-3f, 9.6649509e-3f));
+    q = fma2f(q, u, pk2f(-6.6175476e-2f, -6.6175476e-2f));
+    q = fma2f(q, u, pk2f(3.9884755e-1f, 3.9884755e-1f));
+    const uint64_t phi = fma2f(gc, q, pk2f(0.5f, 0.5f));
+    return mul2f(v, mul2f(gl, phi));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 }  // namespace ptx
 

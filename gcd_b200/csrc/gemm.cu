@@ -104,6 +104,9 @@ struct TcParams {
     int has_r1, has_r2, r1f32, r2f32;
     float a0, a1, a2;
     int of32, geglu, act;
+    double* gn_stats;           // fused GroupNorm statistics of the output (nullptr: off)
+    int gn_cpg, gn_groups;
+    long long gn_rpi;
 };
 
 constexpr int TC_A_BYTES = 128 * 128;
@@ -341,7 +344,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 if (p.geglu) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) xf[j] *= gelu_erf(xf[16 + j]);
+                    for (int j = 0; j < 16; j += 2)
+                        upk2f(geglu_pair(pk2f(xf[j], xf[j + 1]), xf[16 + j], xf[17 + j]), xf[j], xf[j + 1]);
                 }
                 if (p.act == 1) {
 #pragma unroll
@@ -385,6 +389,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tma_store_4d(&mapO, myO, p.geglu ? (n >> 1) : n, tx * TW, ty * TH, tz * TN);
                     bulk_commit();
                     if (has_res) prefetch_residual();         // next chunk of this warpgroup
+                }
+                if (p.gn_stats) {
+                    // Fused GroupNorm statistics: lane = column of the chunk; each warp sums its own 32 staged rows
+                    // (exactly the stored values), then a segmented warp scan folds the columns of each channel group.
+                    const int col = n + lane;
+                    float s1 = 0.f, s2 = 0.f;
+                    if (col < p.N) {
+#pragma unroll 4
+                        for (int rr = 0; rr < 32; rr++) {
+                            const int row = q * 32 + rr;
+                            float val;
+                            if (p.of32) val = *reinterpret_cast<const float*>(myO + stg_off(row, lane >> 2, 8, 0) + (lane & 3) * 4);
+                            else val = act2f(*reinterpret_cast<const act_t*>(myO + stg_off(row, lane >> 3, 4, 1) + (lane & 7) * 2));
+                            s1 += val; s2 += val * val;
+                        }
+                    }
+                    const int gl = col % p.gn_cpg;            // position inside the channel group
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const float t1 = __shfl_up_sync(0xffffffffu, s1, off), t2 = __shfl_up_sync(0xffffffffu, s2, off);
+                        if (gl >= off && lane >= off) { s1 += t1; s2 += t2; }
+                    }
+                    const bool last = (gl == p.gn_cpg - 1) || lane == 31 || col == p.N - 1;
+                    if (last && col < p.N) {
+                        const int64_t row0 = ((int64_t)(tz * TN) * p.Yo + ty * TH) * p.Xo + tx * TW;
+                        double* dst = p.gn_stats + ((row0 / p.gn_rpi) * p.gn_groups + col / p.gn_cpg) * 2;
+                        atomicAdd(dst, (double)s1);
+                        atomicAdd(dst + 1, (double)s2);
+                    }
                 }
             }
             tc_fence_before();
@@ -512,6 +545,15 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     p.has_r1 = e.res1 != nullptr; p.has_r2 = e.res2 != nullptr; p.r1f32 = e.res1_f32; p.r2f32 = e.res2_f32;
     p.a0 = e.a_acc; p.a1 = e.a_res1; p.a2 = e.a_res2;
     p.of32 = e.out_f32; p.geglu = e.geglu; p.act = e.act;
+    int stats_skipped = 0;
+    if (e.gn_stats) {
+        GCD_REQUIRE(e.gn_cpg > 0 && e.gn_groups > 0 && e.gn_rows_per_img > 0 && !e.geglu, "gcd_tc_run: bad gn_stats arguments");
+        const long long rpi = e.gn_rows_per_img, plane = (long long)op->Xo * op->Yo;
+        const bool full = (op->Xo % TW == 0) && (op->Yo % TH == 0) && (op->Zo % TN == 0);
+        const bool one_img = TN == 1 && ((rpi % plane == 0) || (TH == 1 && rpi % TW == 0 && (op->Xo % rpi == 0 || rpi % op->Xo == 0)));
+        if (full && one_img) { p.gn_stats = e.gn_stats; p.gn_cpg = e.gn_cpg; p.gn_groups = e.gn_groups; p.gn_rpi = rpi; }
+        else stats_skipped = 1;
+    }
 
     // ---- tensor maps
     CUtensorMap mA, mB, mO, mR1, mR2;
@@ -551,9 +593,11 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
             if (rc) return rc;
         }
     }
+    int rc;
     switch (BN) {
-        case 256: return launch_tc<256>(mA, mB, mO, mR1, mR2, p, st);
-        case 160: return launch_tc<160>(mA, mB, mO, mR1, mR2, p, st);
-        default: return launch_tc<128>(mA, mB, mO, mR1, mR2, p, st);
+        case 256: rc = launch_tc<256>(mA, mB, mO, mR1, mR2, p, st); break;
+        case 160: rc = launch_tc<160>(mA, mB, mO, mR1, mR2, p, st); break;
+        default: rc = launch_tc<128>(mA, mB, mO, mR1, mR2, p, st); break;
     }
+    return rc ? rc : stats_skipped;
 }

@@ -99,7 +99,7 @@ def _ld(t):
 
 
 def make_ep(out, bias=None, rowvec=None, rows_per_vec=1, res1=None, a_res1=1.0, res2=None, a_res2=1.0, a_acc=1.0,
-            geglu=False, act=0):
+            geglu=False, act=0, gn_stats=None):
     """Fused epilogue descriptor; `out`/`res*` are 2-D [rows, cols] views (row stride = leading dimension)."""
     _need_cuda(out, bias, rowvec, res1, res2)
     e = Epilogue()
@@ -118,6 +118,10 @@ def make_ep(out, bias=None, rowvec=None, rows_per_vec=1, res1=None, a_res1=1.0, 
     e.a_acc, e.a_res1, e.a_res2 = float(a_acc), float(a_res1), float(a_res2)
     e.out, e.ld_out, e.out_f32 = out.data_ptr(), _ld(out), _is_f32(out)
     e.geglu, e.act = int(bool(geglu)), int(act)
+    if gn_stats is not None:      # (float64 buffer [n_img*groups*2] zeroed by the caller, cpg, groups, rows_per_img)
+        buf, cpg, groups, rpi = gn_stats
+        assert buf.dtype == torch.float64 and buf.is_cuda
+        e.gn_stats, e.gn_cpg, e.gn_groups, e.gn_rows_per_img = buf.data_ptr(), int(cpg), int(groups), int(rpi)
     return e
 
 
@@ -139,7 +143,10 @@ def tc_run(A, C, in_ext, in_strides, out_ext, taps, W, ldw, N, ep, in_mul=1, gem
     if _PROF is not None and DETAIL:
         name = f"tc M{op.Xo * op.Yo * op.Zo} N{op.N} K{op.ntaps * op.C} taps{op.ntaps} g{ep.geglu} r{int(bool(ep.res1))}{int(bool(ep.res2))} o{ep.out_f32}"
     with _timed(name, 2.0 * op.Xo * op.Yo * op.Zo * op.N * op.ntaps * op.C):
-        check(lib().gcd_tc_run(ctypes.byref(op), _stream()), "gcd_tc_run")
+        rc = lib().gcd_tc_run(ctypes.byref(op), _stream())
+    if rc < 0:
+        check(rc, "gcd_tc_run")
+    return rc == 0      # False: succeeded, but the requested fused GroupNorm statistics were not produced
 
 
 def linear(x, w, ep):
@@ -148,8 +155,8 @@ def linear(x, w, ep):
     N = w.shape[0]
     assert w.shape[1] == K and w.stride(1) == 1 and x.stride(1) == 1
     sx = x.stride(0)
-    tc_run(x, K, (rows, 1, 1), (sx, sx * rows, sx * rows), (rows, 1, 1), [(0, 0, 0)], w, w.stride(0), N, ep,
-           gemm_tile=True)
+    return tc_run(x, K, (rows, 1, 1), (sx, sx * rows, sx * rows), (rows, 1, 1), [(0, 0, 0)], w, w.stride(0), N, ep,
+                  gemm_tile=True)
 
 
 def bmm_nt(a, b, ep):
@@ -171,30 +178,35 @@ def conv2d_3x3(x, w, ep, stride=1):
     assert x.is_contiguous() and w.shape[1] == 9 * C
     Ho = (H - 1) // stride + 1
     Wo = (W_ - 1) // stride + 1
-    tc_run(x, C, (W_, H, n), (C, W_ * C, H * W_ * C), (Wo, Ho, n), TAPS_3x3, w, w.stride(0), w.shape[0], ep,
-           in_mul=stride)
-    return Ho, Wo
+    return tc_run(x, C, (W_, H, n), (C, W_ * C, H * W_ * C), (Wo, Ho, n), TAPS_3x3, w, w.stride(0), w.shape[0], ep,
+                  in_mul=stride)
 
 
 def conv_t3(x, w, ep):
     """x: act [B, T, HW, C] contiguous; w: act [Cout, 3*C] packed (kt, c). Conv3d kernel (3,1,1), padding (1,0,0)."""
     B, T, HW, C = x.shape
     assert x.is_contiguous() and w.shape[1] == 3 * C
-    tc_run(x, C, (HW, T, B), (C, HW * C, T * HW * C), (HW, T, B), TAPS_T3, w, w.stride(0), w.shape[0], ep)
+    return tc_run(x, C, (HW, T, B), (C, HW * C, T * HW * C), (HW, T, B), TAPS_T3, w, w.stride(0), w.shape[0], ep)
 
 
 # ------------------------------------------------------------------------------------------------ norms
-def groupnorm(x, n_img, rows, C, gamma, beta, eps, silu, out, stats, groups=32):
-    """x: [n_img*rows, C] float32 or act -> out act. stats: float64 scratch [n_img*groups*2]."""
+def zero_stats(stats, n_img, groups=32):
+    check(lib().gcd_memset_async(_p(stats), 0, n_img * groups * 2 * 8, _stream()), "memset")
+
+
+def groupnorm(x, n_img, rows, C, gamma, beta, eps, silu, out, stats, groups=32, have_stats=False):
+    """x: [n_img*rows, C] float32 or act -> out act. stats: float64 scratch [n_img*groups*2]; have_stats=True when a
+    producing tensor-core op already accumulated them (gcd_epilogue.gn_stats)."""
     _need_cuda(x, gamma, beta, out, stats)
     L = lib()
     st = _stream()
     nbytes = n_img * groups * 2 * 8
     assert stats.dtype == torch.float64 and stats.numel() * 8 >= nbytes
     f32 = _is_f32(x)
-    with _timed("groupnorm", 0.0, n_img * rows * C * ((8 if f32 else 4) + 2)):
-        check(L.gcd_memset_async(_p(stats), 0, nbytes, st), "memset")
-        check(L.gcd_groupnorm_stats(_p(x), f32, n_img, rows, C, groups, _p(stats), st), "groupnorm_stats")
+    with _timed("groupnorm", 0.0, n_img * rows * C * (((4 if f32 else 2) * (1 if have_stats else 2)) + 2)):
+        if not have_stats:
+            check(L.gcd_memset_async(_p(stats), 0, nbytes, st), "memset")
+            check(L.gcd_groupnorm_stats(_p(x), f32, n_img, rows, C, groups, _p(stats), st), "groupnorm_stats")
         check(L.gcd_groupnorm_apply(_p(x), f32, n_img, rows, C, groups, _p(stats), _p(gamma), _p(beta), float(eps),
                                     int(bool(silu)), _p(out), st), "groupnorm_apply")
 

@@ -178,9 +178,18 @@ class UNetEngine:
         self.weight_bytes = sum(t.numel() * t.element_size() for t in W.values())
 
     # ------------------------------------------------------------------------------------------------ small helpers
-    def _gn(self, x, n_img, rows, C, name, eps, silu, out):
-        st = self.pool.get("gn_stats", (max(n_img, 64) * 64,), torch.float64)
-        ops.groupnorm(x, n_img, rows, C, self.w[name + ".g"], self.w[name + ".b"], eps, silu, out, st)
+    def _gn(self, x, n_img, rows, C, name, eps, silu, out, stats=None):
+        """GroupNorm(32) (+SiLU) -> act. `stats`: statistics already accumulated by the producing tensor-core op."""
+        st = stats if stats is not None else self.pool.get("gn_stats", (max(n_img, 64) * 64,), torch.float64)
+        ops.groupnorm(x, n_img, rows, C, self.w[name + ".g"], self.w[name + ".b"], eps, silu, out, st,
+                      have_stats=stats is not None)
+
+    def _stats_req(self, n_img, C, rows_per_img):
+        """Zeroed float64 statistics buffer (ring of 8: producer -> next GroupNorm hand-off) + the epilogue descriptor."""
+        self._ring = (getattr(self, "_ring", 0) + 1) % 8
+        st = self.pool.get(f"gn_ring{self._ring}", (max(n_img, 64) * 64,), torch.float64)
+        ops.zero_stats(st, n_img)
+        return st, (st, C // 32, 32, rows_per_img)
 
     def _mlp_small(self, x_act, k0, k2, out_f32, accumulate):
         """Linear -> SiLU -> Linear on a handful of rows (time_embed / label_emb / time_pos_embed)."""
@@ -228,20 +237,22 @@ class UNetEngine:
         return vecs
 
     # ------------------------------------------------------------------------------------------------ blocks
-    def _vrb(self, p, x, cin, cout, n, B, T, H, Wd, emb_all, out=None):
+    def _vrb(self, p, x, cin, cout, n, B, T, H, Wd, emb_all, out=None, x_stats=None):
         """VideoResBlock.forward (video_model.py:62-81) over ResBlock._forward (openaimodel.py:331-357).
-        x: float32 [n*H*W, cin]; returns float32 [n*H*W, cout]."""
+        x: float32 [n*H*W, cin]; returns (float32 [n*H*W, cout], per-frame GroupNorm statistics of it or None).
+        Every conv accumulates the statistics of the GroupNorm that follows it in its epilogue (gcd_epilogue.gn_stats)."""
         W, pool, AD = self.w, self.pool, self.AD
         HW = H * Wd
         rows = n * HW
-        a = pool.get("act_a", (rows, max(cin, cout)), AD)[:, :cin] if False else pool.get(f"act_a{cin}", (rows, cin), AD)
-        self._gn(x, n, HW, cin, p + ".n1", 1e-5, True, a)
+        a = pool.get(f"act_a{cin}", (rows, cin), AD)
+        self._gn(x, n, HW, cin, p + ".n1", 1e-5, True, a, stats=x_stats)
         h1 = pool.get(f"act_h{cout}", (rows, cout), AD)
         eo = self.emb_off[p]
-        ops.conv2d_3x3(a.view(n, H, Wd, cin), W[p + ".c1.w"],
-                       ops.make_ep(h1, bias=W[p + ".c1.b"], rowvec=emb_all[:, eo:eo + cout], rows_per_vec=HW))
+        st, req = self._stats_req(n, cout, HW)
+        ok = ops.conv2d_3x3(a.view(n, H, Wd, cin), W[p + ".c1.w"],
+                            ops.make_ep(h1, bias=W[p + ".c1.b"], rowvec=emb_all[:, eo:eo + cout], rows_per_vec=HW, gn_stats=req))
         a2 = pool.get(f"act_a{cout}", (rows, cout), AD)
-        self._gn(h1, n, HW, cout, p + ".n2", 1e-5, True, a2)
+        self._gn(h1, n, HW, cout, p + ".n2", 1e-5, True, a2, stats=st if ok else None)
         xs = out if out is not None else pool.get(f"vrb_xs{cout}", (rows, cout), torch.float32)
         if cin != cout:
             xa = pool.get(f"act_x{cin}", (rows, cin), AD)
@@ -250,19 +261,23 @@ class UNetEngine:
             res = xs
         else:
             res = x
-        ops.conv2d_3x3(a2.view(n, H, Wd, cout), W[p + ".c2.w"], ops.make_ep(xs, bias=W[p + ".c2.b"], res1=res))
-        # ---- temporal ResBlock (time_stack) + AlphaBlender
+        st, req = self._stats_req(B, cout, T * HW)
+        ok = ops.conv2d_3x3(a2.view(n, H, Wd, cout), W[p + ".c2.w"],
+                            ops.make_ep(xs, bias=W[p + ".c2.b"], res1=res, gn_stats=req))
+        # ---- temporal ResBlock (time_stack) + AlphaBlender; its GroupNorms span (C/32, T, H, W) per clip
         q = p + ".time_stack"
-        self._gn(xs, B, T * HW, cout, q + ".n1", 1e-5, True, a2)
+        self._gn(xs, B, T * HW, cout, q + ".n1", 1e-5, True, a2, stats=st if ok else None)
         eo = self.emb_off[q]
-        ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c1.w"],
-                    ops.make_ep(h1, bias=W[q + ".c1.b"], rowvec=emb_all[:, eo:eo + cout], rows_per_vec=HW))
-        self._gn(h1, B, T * HW, cout, q + ".n2", 1e-5, True, a2)
+        st, req = self._stats_req(B, cout, T * HW)
+        ok = ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c1.w"],
+                         ops.make_ep(h1, bias=W[q + ".c1.b"], rowvec=emb_all[:, eo:eo + cout], rows_per_vec=HW, gn_stats=req))
+        self._gn(h1, B, T * HW, cout, q + ".n2", 1e-5, True, a2, stats=st if ok else None)
         al = self.alpha[p]
         # x = alpha * x_spatial + (1 - alpha) * (x_spatial + conv)  =  x_spatial + (1 - alpha) * conv
-        ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c2.w"],
-                    ops.make_ep(xs, bias=W[q + ".c2.b"], a_acc=1.0 - al, res1=xs, a_res1=1.0))
-        return xs
+        st, req = self._stats_req(n, cout, HW)
+        ok = ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c2.w"],
+                         ops.make_ep(xs, bias=W[q + ".c2.b"], a_acc=1.0 - al, res1=xs, a_res1=1.0, gn_stats=req))
+        return xs, (st if ok else None)
 
     def _ff(self, blk, name, a, rows, C, ep2):
         W = self.w
@@ -270,13 +285,14 @@ class UNetEngine:
         ops.linear(a, W[f"{blk}.{name}.0.w"], ops.make_ep(hid, bias=W[f"{blk}.{name}.0.b"], geglu=True))
         ops.linear(hid, W[f"{blk}.{name}.2.w"], ep2)
 
-    def _svt(self, p, xin, C, n, B, T, S, ca):
-        """SpatialVideoTransformer.forward (video_attention.py:230-301); xin float32 [n*S, C], updated in place."""
+    def _svt(self, p, xin, C, n, B, T, S, ca, x_stats=None):
+        """SpatialVideoTransformer.forward (video_attention.py:230-301); xin float32 [n*S, C], updated in place.
+        Returns (xin, per-frame GroupNorm statistics of the result or None)."""
         W, pool, AD = self.w, self.pool, self.AD
         rows = n * S
         heads = C // 64
         a = pool.get(f"act_a{C}", (rows, C), AD)
-        self._gn(xin, n, S, C, p + ".norm", 1e-6, False, a)
+        self._gn(xin, n, S, C, p + ".norm", 1e-6, False, a, stats=x_stats)
         x = pool.get(f"svt_x{C}", (rows, C), torch.float32)
         ops.linear(a, W[p + ".proj_in.w"], ops.make_ep(x, bias=W[p + ".proj_in.b"]))
         # ---- spatial BasicTransformerBlock (attention.py:551-572)
@@ -306,8 +322,9 @@ class UNetEngine:
         blended = pool.get(f"act_b{C}", (rows, C), AD)
         self._ff(t, "ff", a, rows, C, ops.make_ep(blended, bias=W[t + ".ff.2.b"], a_acc=1.0 - al, res1=xm, a_res1=1.0 - al,
                                                   res2=x, a_res2=al))
-        ops.linear(blended, W[p + ".proj_out.w"], ops.make_ep(xin, bias=W[p + ".proj_out.b"], res1=xin))
-        return xin
+        st, req = self._stats_req(n, C, S)
+        ok = ops.linear(blended, W[p + ".proj_out.w"], ops.make_ep(xin, bias=W[p + ".proj_out.b"], res1=xin, gn_stats=req))
+        return xin, (st if ok else None)
 
     # ------------------------------------------------------------------------------------------------ forward
     def embed(self, timesteps, y):
@@ -343,49 +360,55 @@ class UNetEngine:
         hs = []
         h, hH, hW, hC = None, H, Wd, None
 
-        def run(layers, h, hH, hW, hC, bi, tag):
+        def run(layers, h, hH, hW, hC, bi, tag, hst):
+            """hst: per-frame GroupNorm statistics of h accumulated by its producer (or None)."""
             for kind, p, cin, cout in layers:
                 rows = n * hH * hW
                 if kind == "conv_in":
                     o = pool.get(f"{tag}{bi}", (rows, cout), torch.float32)
-                    ops.conv2d_3x3(x_cl, W[p + ".w"], ops.make_ep(o, bias=W[p + ".b"]))
-                    h, hC = o, cout
+                    st, req = self._stats_req(n, cout, hH * hW)
+                    ok = ops.conv2d_3x3(x_cl, W[p + ".w"], ops.make_ep(o, bias=W[p + ".b"], gn_stats=req))
+                    h, hC, hst = o, cout, (st if ok else None)
                 elif kind == "vrb":
                     o = pool.get(f"{tag}{bi}", (rows, cout), torch.float32)
-                    h = self._vrb(p, h, cin, cout, n, B, T, hH, hW, emb_all, out=o)
+                    h, hst = self._vrb(p, h, cin, cout, n, B, T, hH, hW, emb_all, out=o, x_stats=hst)
                     hC = cout
                 elif kind == "svt":
-                    h = self._svt(p, h, cout, n, B, T, hH * hW, ca)
+                    h, hst = self._svt(p, h, cout, n, B, T, hH * hW, ca, x_stats=hst)
                 elif kind == "down":
                     xa = pool.get(f"act_x{cin}", (rows, cin), AD)
                     ops.cast_to_act(h, xa)
                     Ho, Wo = (hH - 1) // 2 + 1, (hW - 1) // 2 + 1
                     o = pool.get(f"{tag}{bi}", (n * Ho * Wo, cout), torch.float32)
-                    ops.conv2d_3x3(xa.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(o, bias=W[p + ".b"]), stride=2)
-                    h, hH, hW, hC = o, Ho, Wo, cout
+                    st, req = self._stats_req(n, cout, Ho * Wo)
+                    ok = ops.conv2d_3x3(xa.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(o, bias=W[p + ".b"], gn_stats=req),
+                                        stride=2)
+                    h, hH, hW, hC, hst = o, Ho, Wo, cout, (st if ok else None)
                 elif kind == "up":
                     xu = pool.get(f"act_up{cin}", (n * 4 * hH * hW, cin), AD)
                     ops.upsample2x_to_act(h, n, hH, hW, cin, xu)
                     hH, hW = 2 * hH, 2 * hW
                     o = pool.get(f"{tag}{bi}u", (n * hH * hW, cout), torch.float32)
                     ops.conv2d_3x3(xu.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(o, bias=W[p + ".b"]))
-                    h, hC = o, cout
-            return h, hH, hW, hC
+                    h, hC, hst = o, cout, None      # consumed by a channel concat, not by a GroupNorm
+            return h, hH, hW, hC, hst
 
+        hst = None
         for bi, layers in enumerate(inp):
-            h, hH, hW, hC = run(layers, h, hH, hW, hC, bi, "in")
+            h, hH, hW, hC, hst = run(layers, h, hH, hW, hC, bi, "in", hst)
             hs.append((h, hH, hW, hC))
-        h, hH, hW, hC = run(mid, h, hH, hW, hC, 0, "mid")
+        h, hH, hW, hC, hst = run(mid, h, hH, hW, hC, 0, "mid", hst)
         for bi, layers in enumerate(out):
             s, sH, sW, sC = hs.pop()
             if (sH, sW) != (hH, hW):
                 raise ValueError(f"skip/upsample size mismatch {(sH, sW)} vs {(hH, hW)}: latent H, W must be divisible by 8")
             cat = pool.get(f"cat{bi}", (n * hH * hW, hC + sC), torch.float32)
             ops.concat_channels(h, s, cat)
-            h, hH, hW, hC = run(layers, cat, hH, hW, hC + sC, bi, "out")
+            # the concatenated tensor regroups channels: its GroupNorm statistics cannot reuse the producers' sums
+            h, hH, hW, hC, hst = run(layers, cat, hH, hW, hC + sC, bi, "out", None)
         rows = n * hH * hW
         a = pool.get(f"act_a{hC}", (rows, hC), AD)
-        self._gn(h, n, hH * hW, hC, "out.0", 1e-5, True, a)
+        self._gn(h, n, hH * hW, hC, "out.0", 1e-5, True, a, stats=hst)
         res = pool.get("net_out", (rows, 16), torch.float32)
         oc = cfg["out_channels"]
         ops.conv2d_3x3(a.view(n, hH, hW, hC), W["out.2.w"], ops.make_ep(res[:, :oc], bias=W["out.2.b"]))

@@ -73,20 +73,30 @@ class DecoderEngine:
                 W["tmix.b"] = g("conv_out.time_mix_conv.bias").contiguous()
         self.weight_bytes = sum(t.numel() * t.element_size() for t in W.values())
 
-    def _gn(self, x, n_img, rows, C, name, eps, silu, out):
-        st = self.pool.get("gn_stats", (max(n_img, 64) * 64,), torch.float64)
-        ops.groupnorm(x, n_img, rows, C, self.w[name + ".g"], self.w[name + ".b"], eps, silu, out, st)
+    def _gn(self, x, n_img, rows, C, name, eps, silu, out, stats=None):
+        st = stats if stats is not None else self.pool.get("gn_stats", (max(n_img, 64) * 64,), torch.float64)
+        ops.groupnorm(x, n_img, rows, C, self.w[name + ".g"], self.w[name + ".b"], eps, silu, out, st,
+                      have_stats=stats is not None)
 
-    def _res(self, p, x, cin, cout, n, B, T, H, Wd, tag):
-        """temporal_ae.VideoResBlock.forward (temporal_ae.py:64-83) over ResnetBlock.forward (model.py:127-151)."""
+    def _stats_req(self, n_img, C, rows_per_img):
+        """Zeroed statistics buffer for the GroupNorm that consumes the tensor a conv is about to write (fused in its epilogue)."""
+        self._ring = (getattr(self, "_ring", 0) + 1) % 8
+        st = self.pool.get(f"gn_ring{self._ring}", (max(n_img, 64) * 64,), torch.float64)
+        ops.zero_stats(st, n_img)
+        return st, (st, C // 32, 32, rows_per_img)
+
+    def _res(self, p, x, cin, cout, n, B, T, H, Wd, tag, x_stats=None):
+        """temporal_ae.VideoResBlock.forward (temporal_ae.py:64-83) over ResnetBlock.forward (model.py:127-151).
+        Returns (x_out, per-frame GroupNorm statistics of x_out or None)."""
         W, pool, AD = self.w, self.pool, self.AD
         HW, rows = H * Wd, n * H * Wd
         a = pool.get(f"a{cin}_{rows}", (rows, cin), AD)
-        self._gn(x, n, HW, cin, p + ".n1", 1e-6, True, a)
+        self._gn(x, n, HW, cin, p + ".n1", 1e-6, True, a, stats=x_stats)
         h1 = pool.get(f"h{cout}_{rows}", (rows, cout), AD)
-        ops.conv2d_3x3(a.view(n, H, Wd, cin), W[p + ".c1.w"], ops.make_ep(h1, bias=W[p + ".c1.b"]))
+        st, req = self._stats_req(n, cout, HW)
+        ok = ops.conv2d_3x3(a.view(n, H, Wd, cin), W[p + ".c1.w"], ops.make_ep(h1, bias=W[p + ".c1.b"], gn_stats=req))
         a2 = pool.get(f"a{cout}_{rows}", (rows, cout), AD)
-        self._gn(h1, n, HW, cout, p + ".n2", 1e-6, True, a2)
+        self._gn(h1, n, HW, cout, p + ".n2", 1e-6, True, a2, stats=st if ok else None)
         xs = pool.get(f"{tag}_{cout}_{rows}", (rows, cout), torch.float32)
         if cin != cout:
             xa = pool.get(f"xa{cin}_{rows}", (rows, cin), AD)
@@ -95,22 +105,25 @@ class DecoderEngine:
             res = xs
         else:
             res = x
-        ops.conv2d_3x3(a2.view(n, H, Wd, cout), W[p + ".c2.w"], ops.make_ep(xs, bias=W[p + ".c2.b"], res1=res))
+        st, req = self._stats_req(B, cout, T * HW)
+        ok = ops.conv2d_3x3(a2.view(n, H, Wd, cout), W[p + ".c2.w"], ops.make_ep(xs, bias=W[p + ".c2.b"], res1=res, gn_stats=req))
         q = p + ".time_stack"
-        self._gn(xs, B, T * HW, cout, q + ".n1", 1e-5, True, a2)
-        ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c1.w"], ops.make_ep(h1, bias=W[q + ".c1.b"]))
-        self._gn(h1, B, T * HW, cout, q + ".n2", 1e-5, True, a2)
+        self._gn(xs, B, T * HW, cout, q + ".n1", 1e-5, True, a2, stats=st if ok else None)
+        st, req = self._stats_req(B, cout, T * HW)
+        ok = ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c1.w"], ops.make_ep(h1, bias=W[q + ".c1.b"], gn_stats=req))
+        self._gn(h1, B, T * HW, cout, q + ".n2", 1e-5, True, a2, stats=st if ok else None)
         # x = alpha * (x_s + conv) + (1 - alpha) * x_s = x_s + alpha * conv     (temporal_ae.py:79-80)
-        ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c2.w"],
-                    ops.make_ep(xs, bias=W[q + ".c2.b"], a_acc=self.alpha[p], res1=xs))
-        return xs
+        st, req = self._stats_req(n, cout, HW)
+        ok = ops.conv_t3(a2.view(B, T, HW, cout), W[q + ".c2.w"],
+                         ops.make_ep(xs, bias=W[q + ".c2.b"], a_acc=self.alpha[p], res1=xs, gn_stats=req))
+        return xs, (st if ok else None)
 
-    def _attn(self, p, x, C, n, S):
+    def _attn(self, p, x, C, n, S, x_stats=None):
         """AttnBlock (model.py:161-201): out = x + proj_out(softmax(q k^T / sqrt(C)) v), single head, per frame."""
         W, pool, AD = self.w, self.pool, self.AD
         rows = n * S
         a = pool.get(f"a{C}_{rows}", (rows, C), AD)
-        self._gn(x, n, S, C, p + ".norm", 1e-6, False, a)
+        self._gn(x, n, S, C, p + ".norm", 1e-6, False, a, stats=x_stats)
         q = pool.get("attn_q", (rows, C), AD)
         k = pool.get("attn_k", (rows, C), AD)
         ops.linear(a, W[p + ".q.w"], ops.make_ep(q, bias=W[p + ".q.b"]))
@@ -137,27 +150,31 @@ class DecoderEngine:
         W, pool, AD = self.w, self.pool, self.AD
         assert n % T == 0
         B = n // T
-        h, hH, hW, hC = None, H, Wd, None
+        h, hH, hW, hC, hst = None, H, Wd, None, None
         for i, (kind, p, cin, cout) in enumerate(self.plan):
             rows = n * hH * hW
             if kind == "conv_in":
                 h = pool.get(f"s0_{cout}_{rows}", (rows, cout), torch.float32)
-                ops.conv2d_3x3(z_cl, W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"]))
-                hC = cout
+                st, req = self._stats_req(n, cout, hH * hW)
+                ok = ops.conv2d_3x3(z_cl, W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"], gn_stats=req))
+                hC, hst = cout, (st if ok else None)
             elif kind == "res":
-                h = self._res(p, h, cin, cout, n, B, T, hH, hW, f"s{1 + i % 2}")
+                h, hst = self._res(p, h, cin, cout, n, B, T, hH, hW, f"s{1 + i % 2}", x_stats=hst)
                 hC = cout
             elif kind == "attn":
-                h = self._attn(p, h, cin, n, hH * hW)
+                h = self._attn(p, h, cin, n, hH * hW, x_stats=hst)
+                hst = None
             elif kind == "up":
                 xu = pool.get(f"up{cin}_{rows * 4}", (rows * 4, cin), AD)
                 ops.upsample2x_to_act(h, n, hH, hW, cin, xu)
                 hH, hW = 2 * hH, 2 * hW
                 h = pool.get(f"s0_{cout}_{rows * 4}", (rows * 4, cout), torch.float32)
-                ops.conv2d_3x3(xu.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"]))
+                st, req = self._stats_req(n, cout, hH * hW)
+                ok = ops.conv2d_3x3(xu.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"], gn_stats=req))
+                hst = st if ok else None
             elif kind == "out":
                 a = pool.get(f"a{cin}_{rows}", (rows, cin), AD)
-                self._gn(h, n, hH * hW, cin, "norm_out", 1e-6, True, a)
+                self._gn(h, n, hH * hW, cin, "norm_out", 1e-6, True, a, stats=hst)
                 o16 = pool.get(f"out16_{rows}", (rows, 16), torch.float32)
                 ops.conv2d_3x3(a.view(n, hH, hW, cin), W["conv_out.w"], ops.make_ep(o16[:, :cout], bias=W["conv_out.b"]))
                 assert cout == 3, "AE3DConv tail kernel is written for 3 output channels"

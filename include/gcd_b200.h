@@ -52,6 +52,14 @@ typedef struct gcd_epilogue {
     int32_t out_f32;
     int32_t geglu;
     int32_t act;
+    /* Optional fused GroupNorm statistics of the tensor being written (the NEXT GroupNorm's input):
+     * gn_stats[(row / gn_rows_per_img) * gn_groups + col / gn_cpg][0..1] += (sum, sum of squares) of the stored values.
+     * Zero the buffer first. Only produced when every 128-row output tile lies inside one statistics image and all
+     * tiles are full; otherwise gcd_tc_run returns 1 (success, statistics NOT produced: run gcd_groupnorm_stats). */
+    double* gn_stats;
+    int32_t gn_cpg;
+    int32_t gn_groups;
+    int64_t gn_rows_per_img;
 } gcd_epilogue;
 
 /* Generic tcgen05 implicit-GEMM:  acc[r, n] = sum_{tap, c} A[(x,y,z)(r) * in_mul + tap_off(tap), c] * W[n, tap*Cin + c]
@@ -74,6 +82,7 @@ typedef struct gcd_tc_op {
     int32_t N;                 /* accumulator columns */
     gcd_epilogue ep;
 } gcd_tc_op;
+/* returns 0 on success, 1 on success without the requested fused GroupNorm statistics, < 0 on error */
 int gcd_tc_run(const gcd_tc_op* op, void* stream);
 
 /* ---- normalisation (HBM-bound kernels) ------------------------------------------------------------------ */

@@ -240,3 +240,32 @@ def test_attention_spatial(ops, frames, tokens, heads):
     q, k, v = qkv.float().view(frames, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(frames, tokens, C)
     assert relerr(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("out_f32", [True, False])
+def test_fused_groupnorm_stats(ops, out_f32):
+    """gcd_epilogue.gn_stats: the conv epilogue accumulates (sum, sumsq) per (image, group) of the values it stores."""
+    AD = ops.act_dtype()
+    n, H, W, C, Co = 3, 8, 128, 64, 320
+    x = rnd(n, H, W, C, dtype=AD)
+    w = rnd(Co, C, 3, 3, scale=(9 * C) ** -0.5, dtype=AD)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    bias = rnd(Co)
+    out = torch.empty(n * H * W, Co, device="cuda", dtype=torch.float32 if out_f32 else AD)
+    st = torch.zeros(n * 32 * 2, device="cuda", dtype=torch.float64)
+    ok = ops.conv2d_3x3(x, wp, ops.make_ep(out, bias=bias, gn_stats=(st, Co // 32, 32, H * W)))
+    assert ok
+    v = out.double().view(n, H * W, 32, Co // 32)
+    ref = torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1).reshape(-1)
+    assert torch.allclose(st, ref, rtol=1e-5, atol=1e-3)
+    # consumer: GroupNorm with the fused statistics == GroupNorm with its own statistics pass
+    g, b = rnd(Co) * 0.1 + 1, rnd(Co) * 0.1
+    y1 = torch.empty(n * H * W, Co, device="cuda", dtype=AD)
+    y2 = torch.empty_like(y1)
+    ops.groupnorm(out, n, H * W, Co, g, b, 1e-5, True, y1, st, have_stats=True)
+    ops.groupnorm(out, n, H * W, Co, g, b, 1e-5, True, y2, torch.empty(n * 64, device="cuda", dtype=torch.float64))
+    assert relerr(y1, y2) < 1e-5
+    # a tiling that cannot guarantee one image per tile reports "not produced" instead of wrong statistics
+    x2 = rnd(4, 4, 6, 64, dtype=AD)
+    out2 = torch.empty(4 * 4 * 6, Co, device="cuda")
+    assert not ops.conv2d_3x3(x2, wp, ops.make_ep(out2, bias=bias, gn_stats=(st, Co // 32, 32, 24)))
