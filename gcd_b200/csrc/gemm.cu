@@ -111,7 +111,7 @@ struct TcParams {
 
 constexpr int TC_A_BYTES = 128 * 128;
 constexpr int TC_STG_BYTES = 128 * 128;       // one staging tile: 128 rows x <=128 B
-constexpr int TC_SMEM_MAX = 232448 - 2048;    // 227 KB minus alignment slack
+constexpr int TC_SMEM_MAX = 232448;           // 227 KB opt-in maximum per CTA
 
 __device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
 
@@ -146,15 +146,15 @@ __device__ __forceinline__ void add_residual_row(float* xf, const uint8_t* base,
 template <int BN>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapR1,
-               const __grid_constant__ CUtensorMap mapR2, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2,
+               const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapR2, const TcParams p) {
     constexpr int B_BYTES = BN * 128;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];     // SWIZZLE_128B tiles need 1024-byte alignment
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int STAGES = p.stages;
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * TC_A_BYTES;
-    const int OT = p.geglu ? 4096 : (p.of32 ? 16384 : 8192);          // bytes of one output staging tile
+    const int OT = 16384;                                             // bytes of one output staging tile (128 x 128 B)
     const int RT1 = p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0, RT2 = p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0;
     uint8_t* sO = sB + STAGES * B_BYTES;                    // [2 warpgroups][obufs] output staging
     uint8_t* sR1 = sO + 2 * p.obufs * OT;                   // [2] residual 1 (if any)
@@ -267,26 +267,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float* myBias = sBias + g * 256;
         const int bar_id = 1 + g;
 
-        // residual prefetcher (leader only): the warpgroup's next chunk, issued as soon as its buffer is consumed
-        int pf_tile = blockIdx.x, pf_c0 = g * 32;
+        // residual prefetcher (leader only): walks this warpgroup's (tile, span, chunk) sequence one chunk ahead
+        const int pspan = p.of32 ? 32 : (p.geglu ? 128 : 64);
+        int pf_tile = blockIdx.x, pf_s0 = g * pspan, pf_cc = 0;
         auto prefetch_residual = [&]() {
-            while (pf_tile < total) {                                  // skip tiles where this warpgroup has no chunk
+            while (pf_tile < total) {                                  // skip tiles where this warpgroup has no span
                 const int nt = pf_tile % p.n_tiles;
-                if (pf_c0 < BN && nt * BN + pf_c0 < p.N) break;
-                pf_c0 = g * 32; pf_tile += gridDim.x;
+                if (pf_s0 < BN && nt * BN + pf_s0 < p.N) break;
+                pf_s0 = g * pspan; pf_cc = 0; pf_tile += gridDim.x;
             }
             if (pf_tile >= total) return;
             const int nt = pf_tile % p.n_tiles, mt = pf_tile / p.n_tiles;
             const int tx = mt % p.ntx, ty = (mt / p.ntx) % p.nty, tz = mt / (p.ntx * p.nty);
-            const int ncol = nt * BN + pf_c0;
+            const int ncol = nt * BN + pf_s0 + pf_cc;
             mbar_expect_tx(&rfull[g], rbytes);
             if (p.has_r1) tma_load_4d(&mapR1, myR1, &rfull[g], ncol, tx * TW, ty * TH, tz * TN);
             if (p.has_r2) tma_load_4d(&mapR2, myR2, &rfull[g], ncol, tx * TW, ty * TH, tz * TN);
-            pf_c0 += 64;
+            const int width = min(pspan, min(BN - pf_s0, p.N - nt * BN - pf_s0));
+            pf_cc += 32;
+            if (pf_cc >= width) { pf_cc = 0; pf_s0 += 2 * pspan; }
         };
         if (leader && has_res) prefetch_residual();
 
-        uint32_t ci = 0;                            // chunks processed by this warpgroup
+        uint32_t ci = 0, rc = 0;                    // spans / residual chunks processed by this warpgroup
         int it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
             const int as = it & 1;
@@ -311,112 +314,132 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            // Each warpgroup owns alternating column SPANS of the tile; one span = one staging tile = one TMA store with
+            // 128-byte rows whenever possible (32 fp32 / 64 fp16 / 64 GEGLU output columns). Narrow-row stores made the
+            // TMA store engine the bottleneck of the K=320 GEMMs (profiles/r1_notes.md §1, v6).
+            const int span = p.of32 ? 32 : (p.geglu ? 128 : 64);
 #pragma unroll 1
-            for (int c0 = g * 32; c0 < BN && n0 + c0 < p.N; c0 += 64, ci++) {
+            for (int s0 = g * span; s0 < BN && n0 + s0 < p.N; s0 += 2 * span, ci++) {
                 uint8_t* myO = myObase + (p.obufs == 2 ? (ci & 1) * OT : 0);
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
-                float xf[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) xf[j] = __uint_as_float(v[j]);
-                const int n = n0 + c0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {             // bias slice from smem (warp-broadcast reads)
-                    const float4 t = *reinterpret_cast<const float4*>(myBias + c0 + j);
-                    xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
-                }
-                if (rv) {
-                    if (n + 32 <= p.N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n + j));
-                            xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
-                        }
-                    } else {                                  // ragged N tail
-#pragma unroll 1
-                        for (int j = 0; j < p.N - n; j++) {
-                            const float add = rv[n + j];
-#pragma unroll
-                            for (int k = 0; k < 32; k++) if (k == j) xf[k] += add;
-                        }
-                    }
-                }
-                if (p.geglu) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2)
-                        upk2f(geglu_pair(pk2f(xf[j], xf[j + 1]), xf[16 + j], xf[17 + j]), xf[j], xf[j + 1]);
-                }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) xf[j] = silu(xf[j]);
-                }
-                if (p.a0 != 1.0f) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) xf[j] *= p.a0;
-                }
-                if (has_res) {
-                    mbar_wait(&rfull[g], ci & 1);
-                    if (p.has_r1) add_residual_row(xf, myR1, r, p.r1f32, p.a1);
-                    if (p.has_r2) add_residual_row(xf, myR2, r, p.r2f32, p.a2);
-                }
-                if (leader) {                                 // the store that last used myO has drained it
+                const int width = min(span, min(BN - s0, p.N - n0 - s0));      // accumulator columns in this span
+                const bool wide = p.of32 || p.geglu || width > 32;             // 128-byte staging rows (SWIZZLE_128B)
+                if (leader) {                                                  // the store that last used myO has drained it
                     if (p.obufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                 }
-                named_bar_sync(bar_id, 128);                  // B1: myO is free
-                if (p.of32) {
+                named_bar_sync(bar_id, 128);                                   // B1: myO is free
+#pragma unroll 1
+                for (int cc = 0; cc < width; cc += 32) {
+                    const int c0 = s0 + cc;
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    float xf[32];
 #pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        *reinterpret_cast<uint4*>(myO + stg_off(r, c, 8, 0)) =
-                            make_uint4(__float_as_uint(xf[4 * c]), __float_as_uint(xf[4 * c + 1]),
-                                       __float_as_uint(xf[4 * c + 2]), __float_as_uint(xf[4 * c + 3]));
-                } else if (p.geglu) {                         // 16 output columns: 32-byte rows, SWIZZLE_32B
+                    for (int j = 0; j < 32; j++) xf[j] = __uint_as_float(v[j]);
+                    const int n = n0 + c0;
 #pragma unroll
-                    for (int c = 0; c < 2; c++)
-                        *reinterpret_cast<uint4*>(myO + stg_off(r, c, 2, 2)) =
-                            make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
-                                       pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
-                } else {                                      // 32 output columns: 64-byte rows, SWIZZLE_64B
+                    for (int j = 0; j < 32; j += 4) {                          // bias slice from smem (warp-broadcast reads)
+                        const float4 t = *reinterpret_cast<const float4*>(myBias + c0 + j);
+                        xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
+                    }
+                    if (rv) {
+                        if (n + 32 <= p.N) {
 #pragma unroll
-                    for (int c = 0; c < 4; c++)
-                        *reinterpret_cast<uint4*>(myO + stg_off(r, c, 4, 1)) =
-                            make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
-                                       pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
-                }
-                fence_proxy_async_smem();
-                named_bar_sync(bar_id, 128);                  // B2: tile staged; residual buffer fully consumed
-                if (leader) {
-                    tma_store_4d(&mapO, myO, p.geglu ? (n >> 1) : n, tx * TW, ty * TH, tz * TN);
-                    bulk_commit();
-                    if (has_res) prefetch_residual();         // next chunk of this warpgroup
-                }
-                if (p.gn_stats) {
-                    // Fused GroupNorm statistics: lane = column of the chunk; each warp sums its own 32 staged rows
-                    // (exactly the stored values), then a segmented warp scan folds the columns of each channel group.
-                    const int col = n + lane;
-                    float s1 = 0.f, s2 = 0.f;
-                    if (col < p.N) {
-#pragma unroll 4
-                        for (int rr = 0; rr < 32; rr++) {
-                            const int row = q * 32 + rr;
-                            float val;
-                            if (p.of32) val = *reinterpret_cast<const float*>(myO + stg_off(row, lane >> 2, 8, 0) + (lane & 3) * 4);
-                            else val = act2f(*reinterpret_cast<const act_t*>(myO + stg_off(row, lane >> 3, 4, 1) + (lane & 7) * 2));
-                            s1 += val; s2 += val * val;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+                                xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
+                            }
+                        } else {                                               // ragged N tail
+#pragma unroll 1
+                            for (int j = 0; j < p.N - n; j++) {
+                                const float add = rv[n + j];
+#pragma unroll
+                                for (int k = 0; k < 32; k++) if (k == j) xf[k] += add;
+                            }
                         }
                     }
-                    const int gl = col % p.gn_cpg;            // position inside the channel group
+                    if (p.geglu) {
 #pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const float t1 = __shfl_up_sync(0xffffffffu, s1, off), t2 = __shfl_up_sync(0xffffffffu, s2, off);
-                        if (gl >= off && lane >= off) { s1 += t1; s2 += t2; }
+                        for (int j = 0; j < 16; j += 2)
+                            upk2f(geglu_pair(pk2f(xf[j], xf[j + 1]), xf[16 + j], xf[17 + j]), xf[j], xf[j + 1]);
                     }
-                    const bool last = (gl == p.gn_cpg - 1) || lane == 31 || col == p.N - 1;
-                    if (last && col < p.N) {
-                        const int64_t row0 = ((int64_t)(tz * TN) * p.Yo + ty * TH) * p.Xo + tx * TW;
-                        double* dst = p.gn_stats + ((row0 / p.gn_rpi) * p.gn_groups + col / p.gn_cpg) * 2;
-                        atomicAdd(dst, (double)s1);
-                        atomicAdd(dst + 1, (double)s2);
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) xf[j] = silu(xf[j]);
+                    }
+                    if (p.a0 != 1.0f) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) xf[j] *= p.a0;
+                    }
+                    if (has_res) {
+                        mbar_wait(&rfull[g], rc & 1);
+                        rc++;
+                        if (p.has_r1) add_residual_row(xf, myR1, r, p.r1f32, p.a1);
+                        if (p.has_r2) add_residual_row(xf, myR2, r, p.r2f32, p.a2);
+                        if (cc + 32 < width) {                                 // more chunks in this span: recycle the buffer now
+                            named_bar_sync(bar_id, 128);
+                            if (leader) prefetch_residual();
+                        }
+                    }
+                    if (p.of32) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            *reinterpret_cast<uint4*>(myO + stg_off(r, c, 8, 0)) =
+                                make_uint4(__float_as_uint(xf[4 * c]), __float_as_uint(xf[4 * c + 1]),
+                                           __float_as_uint(xf[4 * c + 2]), __float_as_uint(xf[4 * c + 3]));
+                    } else if (p.geglu) {                      // 16 output columns of a 64-column (128-byte) row
+#pragma unroll
+                        for (int c = 0; c < 2; c++)
+                            *reinterpret_cast<uint4*>(myO + stg_off(r, (cc >> 5) * 2 + c, 8, 0)) =
+                                make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
+                                           pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
+                    } else {                                   // 32 output columns: half of a 128-byte row, or a 64-byte row
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            *reinterpret_cast<uint4*>(myO + (wide ? stg_off(r, (cc >> 5) * 4 + c, 8, 0) : stg_off(r, c, 4, 1))) =
+                                make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
+                                           pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);                  // B2: span staged; residual buffer fully consumed
+                if (leader) {
+                    const int ncol = p.geglu ? ((n0 + s0) >> 1) : (n0 + s0);
+                    tma_store_4d(wide ? &mapO : &mapO2, myO, ncol, tx * TW, ty * TH, tz * TN);
+                    bulk_commit();
+                    if (has_res) prefetch_residual();         // first chunk of this warpgroup's next span
+                }
+                if (p.gn_stats) {
+                    // Fused GroupNorm statistics: lane = column of a 32-column chunk; each warp sums its own 32 staged
+                    // rows (exactly the stored values), then a segmented warp scan folds the columns of each group.
+#pragma unroll 1
+                    for (int cc = 0; cc < width; cc += 32) {
+                        const int col = n0 + s0 + cc + lane;
+                        float s1 = 0.f, s2 = 0.f;
+                        if (col < p.N) {
+#pragma unroll 4
+                            for (int rr = 0; rr < 32; rr++) {
+                                const int row = q * 32 + rr;
+                                float val;
+                                if (p.of32) val = *reinterpret_cast<const float*>(myO + stg_off(row, lane >> 2, 8, 0) + (lane & 3) * 4);
+                                else if (wide) val = act2f(*reinterpret_cast<const act_t*>(myO + stg_off(row, (cc + lane) >> 3, 8, 0) + (lane & 7) * 2));
+                                else val = act2f(*reinterpret_cast<const act_t*>(myO + stg_off(row, lane >> 3, 4, 1) + (lane & 7) * 2));
+                                s1 += val; s2 += val * val;
+                            }
+                        }
+                        const int gl = col % p.gn_cpg;        // position inside the channel group
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const float t1 = __shfl_up_sync(0xffffffffu, s1, off), t2 = __shfl_up_sync(0xffffffffu, s2, off);
+                            if (gl >= off && lane >= off) { s1 += t1; s2 += t2; }
+                        }
+                        const bool last = (gl == p.gn_cpg - 1) || lane == 31 || col == p.N - 1;
+                        if (last && col < p.N) {
+                            const int64_t row0 = ((int64_t)(tz * TN) * p.Yo + ty * TH) * p.Xo + tx * TW;
+                            double* dst = p.gn_stats + ((row0 / p.gn_rpi) * p.gn_groups + col / p.gn_cpg) * 2;
+                            atomicAdd(dst, (double)s1);
+                            atomicAdd(dst + 1, (double)s2);
+                        }
                     }
                 }
             }
@@ -442,32 +465,32 @@ static int ilog2(int v) {
 }
 
 template <int BN>
-static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mR1,
-                     const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mO2,
+                     const CUtensorMap& mR1, const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
     static bool configured = false;
     static int num_sms = 0;
     constexpr int STAGE_BYTES = TC_A_BYTES + BN * 128;
     if (!configured) {
-        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX + 2048));
+        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         int dev = 0;
         GCD_CUDA_CHECK(cudaGetDevice(&dev));
         GCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
-    const int OT = p.geglu ? 4096 : (p.of32 ? 16384 : 8192);
+    const int OT = 16384;
     const int RT = (p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0) + (p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0);
     const int kiters = p.ntaps * p.kchunks;
     // short K loop => the epilogue is the critical path: double-buffer its staging tiles if >= 3 pipeline stages remain
-    p.obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * RT) - 2560) / STAGE_BYTES >= 3) ? 2 : 1;
+    p.obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * RT) - 2304) / STAGE_BYTES >= 3) ? 2 : 1;
     const int epi = 2 * p.obufs * OT + 2 * RT + 2048 /*bias*/;
-    int stages = (TC_SMEM_MAX - epi - 512) / STAGE_BYTES;
+    int stages = (TC_SMEM_MAX - epi - 256) / STAGE_BYTES;
     if (stages > 8) stages = 8;
     GCD_REQUIRE(stages >= 2, "tc_gemm: not enough shared memory for the pipeline (BN=%d)", BN);
     p.stages = stages;
-    const int smem = stages * STAGE_BYTES + epi + 512 + 1024;
+    const int smem = stages * STAGE_BYTES + epi + 256;
     const int total = p.ntx * p.nty * p.ntz * p.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
-    tc_gemm_kernel<BN><<<grid, 384, smem, st>>>(mA, mB, mO, mR1, mR2, p);
+    tc_gemm_kernel<BN><<<grid, 384, smem, st>>>(mA, mB, mO, mO2, mR1, mR2, p);
     GCD_CUDA_CHECK(cudaGetLastError());
     g_launches++;
     return 0;
@@ -495,8 +518,8 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     GCD_REQUIRE(((uintptr_t)op->A & 15) == 0 && ((uintptr_t)op->W & 15) == 0, "gcd_tc_run: operands must be 16B aligned");
     GCD_REQUIRE(op->in_mul == 1 || op->in_mul == 2, "gcd_tc_run: in_mul must be 1 or 2");
     const gcd_epilogue& e = op->ep;
-    GCD_REQUIRE(!e.geglu || (op->N % 32 == 0 && !e.out_f32 && !e.res1 && !e.res2),
-                "gcd_tc_run: GEGLU needs N %% 32 == 0, 16-bit output and no residual");
+    GCD_REQUIRE(!e.geglu || (op->N % 256 == 0 && !e.out_f32 && !e.res1 && !e.res2),
+                "gcd_tc_run: GEGLU needs N %% 256 == 0, 16-bit output and no residual");
     GCD_REQUIRE(!e.rowvec || e.rows_per_vec > 0, "gcd_tc_run: rows_per_vec must be > 0");
     GCD_REQUIRE(!e.bias || ((uintptr_t)e.bias & 15) == 0, "gcd_tc_run: bias must be 16B aligned");
     GCD_REQUIRE(!e.rowvec || (((uintptr_t)e.rowvec & 15) == 0 && e.ld_rowvec % 4 == 0),
@@ -556,7 +579,7 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     }
 
     // ---- tensor maps
-    CUtensorMap mA, mB, mO, mR1, mR2;
+    CUtensorMap mA, mB, mO, mO2, mR1, mR2;
     {
         uint64_t dims[4] = {(uint64_t)op->C, (uint64_t)op->Xi, (uint64_t)op->Yi, (uint64_t)op->Zi};
         uint64_t str[3] = {(uint64_t)op->sx * 2, (uint64_t)op->sy * 2, (uint64_t)op->sz * 2};
@@ -581,8 +604,14 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     }
     {
         const int Nout = e.geglu ? op->N / 2 : op->N;
-        int rc = make_out_map(&mO, e.out, e.out_f32, e.ld_out, Nout, op->Xo, op->Yo, op->Zo, TW, TH, TN, e.geglu ? 16 : 32, "out");
+        // full-width staging tile: 128-byte rows = 32 fp32 / 64 fp16 (incl. GEGLU) columns; mO2: ragged 32-column fp16 span
+        int rc = make_out_map(&mO, e.out, e.out_f32, e.ld_out, Nout, op->Xo, op->Yo, op->Zo, TW, TH, TN, e.out_f32 ? 32 : 64, "out");
         if (rc) return rc;
+        mO2 = mO;
+        if (!e.out_f32 && !e.geglu) {
+            rc = make_out_map(&mO2, e.out, 0, e.ld_out, Nout, op->Xo, op->Yo, op->Zo, TW, TH, TN, 32, "out");
+            if (rc) return rc;
+        }
         mR1 = mO; mR2 = mO;
         if (e.res1) {
             rc = make_out_map(&mR1, e.res1, e.res1_f32, e.ld_res1, op->N, op->Xo, op->Yo, op->Zo, TW, TH, TN, 32, "res1");
@@ -595,9 +624,9 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     }
     int rc;
     switch (BN) {
-        case 256: rc = launch_tc<256>(mA, mB, mO, mR1, mR2, p, st); break;
-        case 160: rc = launch_tc<160>(mA, mB, mO, mR1, mR2, p, st); break;
-        default: rc = launch_tc<128>(mA, mB, mO, mR1, mR2, p, st); break;
+        case 256: rc = launch_tc<256>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 160: rc = launch_tc<160>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        default: rc = launch_tc<128>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
     }
     return rc ? rc : stats_skipped;
 }
