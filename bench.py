@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--workload", default="kubric", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for ncu: exactly --warmup/--steps resident steps, no e2e / instrumented / CPU passes, no JSON claims")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -224,6 +226,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    if args.profile_run:
+        for _ in range(args.warmup):
+            step_resident()
+        ms = timed(step_resident, args.steps)
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms / args.steps}))
+        return
     for _ in range(max(args.warmup, 3)):
         step_resident()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -250,9 +259,13 @@ def main():
         tc_tflops = tc["flops"] / (tc["ms"] / 1e3) / 1e12
         per_frame = flops.clip_flops(unet_cfg, vae_cfg, T_FRAMES, LAT_H, LAT_W, wl["steps"]) / T_FRAMES
         path_tflops = per_frame * (value / world) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))       # dram bytes of one representative tc_gemm launch from `ncu --set full`
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv / linear)",
                 "achieved": round(tc_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(tc_tflops / pk["tflops"], 4),
-                "traffic": None, "peak_source": pk["src"],
+                "traffic": traffic, "peak_source": pk["src"],
                 "kernel_share_of_step": round(tc["ms"] / max(tot_ms, 1e-9), 4),
                 "whole_path": {"algorithmic_tflop_per_latent_frame": round(per_frame / 1e12, 1),
                                "achieved": round(path_tflops, 1), "frac": round(path_tflops / pk["tflops"], 4)},

@@ -21,6 +21,7 @@
 #include "../../include/gcd_b200.h"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 
@@ -143,7 +144,10 @@ __device__ __forceinline__ void add_residual_row(float* xf, const uint8_t* base,
     }
 }
 
-template <int BN>
+// CL = CTAs per cluster (1 or 2). CL == 2: the two CTAs work on adjacent M-tiles of the same N-tile; each loads one
+// half of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the L2 -> SM weight traffic
+// (the level-1 convs / K=320 GEMMs were bound by it: profiles/r1_ncu_prof_conv.txt, lts 62 %). MMAs stay 1-CTA.
+template <int BN, int CL>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2,
@@ -176,10 +180,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         prefetch_tmap(&mapB);
         prefetch_tmap(&mapO);
     }
+    const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; i++) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], CL);      // a multicast stage is free once BOTH CTAs' MMAs have drained it
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
@@ -190,12 +195,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    if (CL == 2) cluster_sync_all(); else __syncthreads();     // barrier inits visible cluster-wide before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Persistent schedule over (M-tile group, N-tile): a cluster takes CL adjacent M-tiles of one N-tile. `tile` below is
+    // a group index; mt may point one past the last M-tile (phantom tile: all loads zero-fill, all stores are clipped).
     const int m_tiles = p.ntx * p.nty * p.ntz;
-    const int total = m_tiles * p.n_tiles;
+    const int total = ((m_tiles + CL - 1) / CL) * p.n_tiles;
+    const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
     const int kiters = p.ntaps * p.kchunks;
     const int TW = 1 << p.lTW, TH = 1 << p.lTH;
     const int TN = 128 >> (p.lTW + p.lTH);
@@ -205,9 +213,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // ===================== TMA producer =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            for (int tile = tile0; tile < total; tile += tile_step) {
                 const int nt = tile % p.n_tiles;
-                const int mt = tile / p.n_tiles;
+                const int mt = (tile / p.n_tiles) * CL + crank;
                 const int tx = mt % p.ntx;
                 const int ty = (mt / p.ntx) % p.nty;
                 const int tz = mt / (p.ntx * p.nty);
@@ -220,7 +228,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_expect_tx(&full[stage], TC_A_BYTES + B_BYTES);
                         tma_load_4d(&mapA, sA + stage * TC_A_BYTES, &full[stage], kc * 64, cx, cy, cz);
-                        tma_load_3d(&mapB, sB + stage * B_BYTES, &full[stage], kidx, nt * BN, wy);
+                        if (CL == 2)       // my half of the weight tile -> both CTAs
+                            tma_load_3d_mc(&mapB, sB + stage * B_BYTES + crank * (B_BYTES / 2), &full[stage], kidx,
+                                           nt * BN + crank * (BN / 2), wy, (uint16_t)0x3);
+                        else
+                            tma_load_3d(&mapB, sB + stage * B_BYTES, &full[stage], kidx, nt * BN, wy);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -233,7 +245,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+            for (int tile = tile0; tile < total; tile += tile_step, it++) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tempty[as], aphase ^ 1);
@@ -247,7 +259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; k++)   // 4 x (K=16) inside the 64-wide swizzle atom: +32 B each
                         umma_f16_ss(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ki | k) != 0);
-                    umma_commit(&empty[stage]);
+                    if (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)0x3); else umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[as]);
@@ -269,15 +281,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
         // residual prefetcher (leader only): walks this warpgroup's (tile, span, chunk) sequence one chunk ahead
         const int pspan = p.of32 ? 32 : (p.geglu ? 128 : 64);
-        int pf_tile = blockIdx.x, pf_s0 = g * pspan, pf_cc = 0;
+        int pf_tile = tile0, pf_s0 = g * pspan, pf_cc = 0;
         auto prefetch_residual = [&]() {
             while (pf_tile < total) {                                  // skip tiles where this warpgroup has no span
                 const int nt = pf_tile % p.n_tiles;
                 if (pf_s0 < BN && nt * BN + pf_s0 < p.N) break;
-                pf_s0 = g * pspan; pf_cc = 0; pf_tile += gridDim.x;
+                pf_s0 = g * pspan; pf_cc = 0; pf_tile += tile_step;
             }
             if (pf_tile >= total) return;
-            const int nt = pf_tile % p.n_tiles, mt = pf_tile / p.n_tiles;
+            const int nt = pf_tile % p.n_tiles, mt = (pf_tile / p.n_tiles) * CL + crank;
             const int tx = mt % p.ntx, ty = (mt / p.ntx) % p.nty, tz = mt / (p.ntx * p.nty);
             const int ncol = nt * BN + pf_s0 + pf_cc;
             mbar_expect_tx(&rfull[g], rbytes);
@@ -291,11 +303,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
         uint32_t ci = 0, rc = 0;                    // spans / residual chunks processed by this warpgroup
         int it = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+        for (int tile = tile0; tile < total; tile += tile_step, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int nt = tile % p.n_tiles;
-            const int mt = tile / p.n_tiles;
+            const int mt = (tile / p.n_tiles) * CL + crank;
             const int tx = mt % p.ntx;
             const int ty = (mt / p.ntx) % p.nty;
             const int tz = mt / (p.ntx * p.nty);
@@ -409,7 +421,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     bulk_commit();
                     if (has_res) prefetch_residual();         // first chunk of this warpgroup's next span
                 }
-                if (p.gn_stats) {
+                if (p.gn_stats && mt < m_tiles) {
                     // Fused GroupNorm statistics: lane = column of a 32-column chunk; each warp sums its own 32 staged
                     // rows (exactly the stored values), then a segmented warp scan folds the columns of each group.
 #pragma unroll 1
@@ -450,7 +462,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CL == 2) cluster_sync_all(); else __syncthreads();     // no CTA leaves while its peer can still signal / write into it
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -464,14 +476,14 @@ static int ilog2(int v) {
     return l;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mO2,
                      const CUtensorMap& mR1, const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
     static bool configured = false;
     static int num_sms = 0;
     constexpr int STAGE_BYTES = TC_A_BYTES + BN * 128;
     if (!configured) {
-        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         int dev = 0;
         GCD_CUDA_CHECK(cudaGetDevice(&dev));
         GCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -488,10 +500,22 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     GCD_REQUIRE(stages >= 2, "tc_gemm: not enough shared memory for the pipeline (BN=%d)", BN);
     p.stages = stages;
     const int smem = stages * STAGE_BYTES + epi + 256;
-    const int total = p.ntx * p.nty * p.ntz * p.n_tiles;
-    const int grid = total < num_sms ? total : num_sms;
-    tc_gemm_kernel<BN><<<grid, 384, smem, st>>>(mA, mB, mO, mO2, mR1, mR2, p);
-    GCD_CUDA_CHECK(cudaGetLastError());
+    const int m_tiles = p.ntx * p.nty * p.ntz;
+    const int groups = ((m_tiles + CL - 1) / CL) * p.n_tiles;
+    const int max_clusters = num_sms / CL;
+    const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GCD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CL>, mA, mB, mO, mO2, mR1, mR2, p));
     g_launches++;
     return 0;
 }
@@ -563,6 +587,9 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     else if (op->N % 160 == 0) BN = 160;
     else BN = 128;
     p.n_tiles = (op->N + BN - 1) / BN;
+    // 2-CTA clusters with multicast weights unless disabled (GCD_TC_CLUSTER=0), batched weights, or a single M-tile
+    static const int cluster_env = [] { const char* e = getenv("GCD_TC_CLUSTER"); return e ? atoi(e) : 2; }();
+    const int CL = (cluster_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? 2 : 1;
 
     p.bias = e.bias; p.rowvec = e.rowvec; p.rpv = e.rows_per_vec; p.ldv = e.ld_rowvec;
     p.has_r1 = e.res1 != nullptr; p.has_r2 = e.res2 != nullptr; p.r1f32 = e.res1_f32; p.r2f32 = e.res2_f32;
@@ -598,7 +625,7 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
         GCD_REQUIRE(op->C % 64 == 0 || op->ntaps == 1, "gcd_tc_run: multi-tap ops need C %% 64 == 0 (got %d)", op->C);
         uint64_t dims[3] = {(uint64_t)op->ntaps * (uint64_t)op->C, (uint64_t)op->N, nb};
         uint64_t str[2] = {(uint64_t)op->ldw * 2, (uint64_t)(p.w_batched ? op->w_batch_stride : op->ldw * (int64_t)op->N) * 2};
-        uint32_t box[3] = {64, (uint32_t)BN, 1};
+        uint32_t box[3] = {64, (uint32_t)(BN / CL), 1};     // CL == 2: each CTA fetches half of the weight tile
         int rc = gcd_make_tmap(&mB, op->W, 3, dims, str, box, nullptr, 128, 0);
         if (rc) return rc;
     }
@@ -623,10 +650,13 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
         }
     }
     int rc;
-    switch (BN) {
-        case 256: rc = launch_tc<256>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 160: rc = launch_tc<160>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        default: rc = launch_tc<128>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+    switch (BN * 10 + CL) {
+        case 2562: rc = launch_tc<256, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 1602: rc = launch_tc<160, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 1282: rc = launch_tc<128, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 2561: rc = launch_tc<256, 1>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 1601: rc = launch_tc<160, 1>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        default: rc = launch_tc<128, 1>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
     }
     return rc ? rc : stats_skipped;
 }
