@@ -86,7 +86,9 @@ def cpu_oracle_sample(unet_cfg, vae_cfg, steps, unet_state=None, vae_state=None,
     the full workload by the exact algorithmic-FLOP ratio. Returns (latent_frames_per_s, description, cores)."""
     from gcd_b200 import flops, spec, synthetic
     from oracle import gcd_oracle as O
-    cores = os.cpu_count() or 1
+    # Measured on the pool's 128-vCPU B200 hosts (tools/cpu_threads.py, same UNet sample): 16 threads 1.9 s, 32 threads
+    # 2.1 s, 64 threads 3.9 s, 128 threads 121 s (the cgroup quota is far below 128 cores) -> use the fastest setting.
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     if unet_state is None:
         unet_state = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
