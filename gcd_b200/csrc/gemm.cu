@@ -144,23 +144,30 @@ __device__ __forceinline__ void add_residual_row(float* xf, const uint8_t* base,
     }
 }
 
-// CL = CTAs per cluster (1 or 2). CL == 2: the two CTAs work on adjacent M-tiles of the same N-tile; each loads one
-// half of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the L2 -> SM weight traffic
-// (the level-1 convs / K=320 GEMMs were bound by it: profiles/r1_ncu_prof_conv.txt, lts 62 %). MMAs stay 1-CTA.
-template <int BN, int CL>
+// MODE 1: one CTA per tile. MODE 2: 2-CTA cluster on adjacent M-tiles of one N-tile; each CTA loads half of the weight
+// tile and TMA-multicasts it into both CTAs' shared memory (halves the L2 -> SM weight traffic; the level-1 convs / K=320
+// GEMMs were bound by it: profiles/r1_ncu_prof_conv.txt, lts 62 %); MMAs stay 1-CTA. MODE 3: CTA pair with
+// tcgen05.mma.cta_group::2 — ONE M=256 MMA per pair issued by the leader CTA, each CTA keeps only its half of the weight
+// tile in smem (also halves the smem operand reads per FLOP: a 1-CTA M128xN160 MMA needs 115 of the 128 B/clk).
+// KC = 64-wide K chunks per pipeline stage: 2 for narrow tiles (BN <= 160), whose 4 MMAs per chunk (320 cycles) are
+// shorter than the issuing thread's per-stage overhead (mbarrier wait + fence + commit) — measured: BN=160 tiles
+// plateaued at 1.12 PFLOP/s in every mode while BN=256 reached 1.45-1.54 (tools/bench_convgemm.py).
+template <int BN, int MODE, int KC>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2,
                const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapR2, const TcParams p) {
-    constexpr int B_BYTES = BN * 128;
+    constexpr int CL = MODE >= 2 ? 2 : 1;
+    constexpr bool PAIR = MODE == 3;
+    constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;     // weight rows held per CTA and stage
     extern __shared__ __align__(1024) uint8_t smem[];     // SWIZZLE_128B tiles need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int STAGES = p.stages;
-    uint8_t* sA = smem;
-    uint8_t* sB = sA + STAGES * TC_A_BYTES;
+    uint8_t* sA = smem;                                    // [STAGES][KC][16 KB]
+    uint8_t* sB = sA + STAGES * KC * TC_A_BYTES;           // [STAGES][KC][B_BYTES]
     const int OT = 16384;                                             // bytes of one output staging tile (128 x 128 B)
     const int RT1 = p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0, RT2 = p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0;
-    uint8_t* sO = sB + STAGES * B_BYTES;                    // [2 warpgroups][obufs] output staging
+    uint8_t* sO = sB + STAGES * KC * B_BYTES;               // [2 warpgroups][obufs] output staging
     uint8_t* sR1 = sO + 2 * p.obufs * OT;                   // [2] residual 1 (if any)
     uint8_t* sR2 = sR1 + 2 * RT1;                           // [2] residual 2 (if any)
     float* sBias = reinterpret_cast<float*>(sR2 + 2 * RT2); // [2][256] bias slice of the current tile, per warpgroup
@@ -184,16 +191,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; i++) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], CL);      // a multicast stage is free once BOTH CTAs' MMAs have drained it
+            mbar_init(&empty[i], MODE == 2 ? 2 : 1);   // MODE 2: a multicast stage is free once BOTH CTAs' MMAs drained it
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 256);
+            mbar_init(&tempty[i], PAIR ? 512 : 256);   // PAIR: the leader's MMA waits for both CTAs' epilogues
             mbar_init(&rfull[i], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) { if (PAIR) tmem_alloc_2cta(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
     if (CL == 2) cluster_sync_all(); else __syncthreads();     // barrier inits visible cluster-wide before any remote arrive
     tc_fence_after();
@@ -221,27 +228,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int tz = mt / (p.ntx * p.nty);
                 const int x0 = tx * TW * p.in_mul, y0 = ty * TH * p.in_mul, z0 = tz * TN;
                 const int wy = p.w_batched ? ty : 0;
-                int kidx = 0;
-                for (int tap = 0; tap < p.ntaps; tap++) {
-                    const int cx = x0 + p.tdx[tap], cy = y0 + p.tdy[tap], cz = z0 + p.tdz[tap];
-                    for (int kc = 0; kc < p.kchunks; kc++, kidx += 64) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], TC_A_BYTES + B_BYTES);
-                        tma_load_4d(&mapA, sA + stage * TC_A_BYTES, &full[stage], kc * 64, cx, cy, cz);
-                        if (CL == 2)       // my half of the weight tile -> both CTAs
-                            tma_load_3d_mc(&mapB, sB + stage * B_BYTES + crank * (B_BYTES / 2), &full[stage], kidx,
-                                           nt * BN + crank * (BN / 2), wy, (uint16_t)0x3);
-                        else
-                            tma_load_3d(&mapB, sB + stage * B_BYTES, &full[stage], kidx, nt * BN, wy);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                const int ntile_w = min(BN, ((p.N - nt * BN) + 15) & ~15);     // width of this N-tile (see MMA issuer)
+                // flattened (tap, channel-chunk) sequence, KC chunks per stage
+                for (int q0 = 0; q0 < kiters; q0 += KC) {
+                    const int nch = min(KC, kiters - q0);
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (PAIR) { if (crank == 0) mbar_expect_tx(&full[stage], 2 * nch * (TC_A_BYTES + B_BYTES)); }
+                    else mbar_expect_tx(&full[stage], nch * (TC_A_BYTES + B_BYTES));
+                    for (int c = 0; c < nch; c++) {
+                        const int qq = q0 + c;
+                        const int tap = qq / p.kchunks, kc = qq - tap * p.kchunks;
+                        const int cx = x0 + p.tdx[tap], cy = y0 + p.tdy[tap], cz = z0 + p.tdz[tap];
+                        uint8_t* dA = sA + (stage * KC + c) * TC_A_BYTES;
+                        uint8_t* dB = sB + (stage * KC + c) * B_BYTES;
+                        if (PAIR) {        // both CTAs' bytes are reported to the leader's barrier
+                            tma_load_4d_2sm(&mapA, dA, &full[stage], kc * 64, cx, cy, cz);
+                            tma_load_3d_2sm(&mapB, dB, &full[stage], qq * 64, nt * BN + crank * (ntile_w / 2), wy);
+                        } else {
+                            tma_load_4d(&mapA, dA, &full[stage], kc * 64, cx, cy, cz);
+                            if (CL == 2)   // my half of the weight tile -> both CTAs
+                                tma_load_3d_mc(&mapB, dB + crank * (B_BYTES / 2), &full[stage], qq * 64,
+                                               nt * BN + crank * (BN / 2), wy, (uint16_t)0x3);
+                            else
+                                tma_load_3d(&mapB, dB, &full[stage], qq * 64, nt * BN, wy);
+                        }
                     }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = make_idesc_f16(128, BN, 0, 0);
+        if (lane == 0 && !(PAIR && crank != 0)) {
+            // ===================== MMA issuer (PAIR: leader CTA only) =====================
+            // the last N-tile of a row may be narrower than BN: issue its MMAs with the actual width (multiple of 16)
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -251,18 +270,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * 256;
-                for (int ki = 0; ki < kiters; ki++) {
+                const int ntile = min(BN, ((p.N - (tile % p.n_tiles) * BN) + 15) & ~15);
+                const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, (uint32_t)ntile, 0, 0);
+                for (int q0 = 0; q0 < kiters; q0 += KC) {
+                    const int nch = min(KC, kiters - q0);
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t ad = make_desc_sw128(smem_u32(sA + stage * TC_A_BYTES), 16, 1024);
-                    const uint64_t bd = make_desc_sw128(smem_u32(sB + stage * B_BYTES), 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)   // 4 x (K=16) inside the 64-wide swizzle atom: +32 B each
-                        umma_f16_ss(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ki | k) != 0);
-                    if (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)0x3); else umma_commit(&empty[stage]);
+                    for (int c = 0; c < KC; c++) {
+                        if (c < nch) {
+                            const uint64_t ad = make_desc_sw128(smem_u32(sA + (stage * KC + c) * TC_A_BYTES), 16, 1024);
+                            const uint64_t bd = make_desc_sw128(smem_u32(sB + (stage * KC + c) * B_BYTES), 16, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) { // 4 x (K=16) inside the 64-wide swizzle atom: +32 B each
+                                const uint32_t acc = (q0 + c + k) != 0;
+                                if (PAIR) umma_f16_ss_2cta(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, acc);
+                                else umma_f16_ss(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, acc);
+                            }
+                        }
+                    }
+                    if (PAIR) umma_commit_2cta_mc(&empty[stage], (uint16_t)0x3);
+                    else if (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)0x3);
+                    else umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[as]);
+                if (PAIR) umma_commit_2cta_mc(&tfull[as], (uint16_t)0x3); else umma_commit(&tfull[as]);
             }
         }
     } else if (warp >= 4) {
@@ -456,7 +488,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[as]);
+            if (PAIR) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
         }
         if (leader) bulk_wait_read<0>();
     }
@@ -465,7 +497,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (CL == 2) cluster_sync_all(); else __syncthreads();     // no CTA leaves while its peer can still signal / write into it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -476,14 +508,18 @@ static int ilog2(int v) {
     return l;
 }
 
-template <int BN, int CL>
+template <int BN, int MODE>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mO2,
                      const CUtensorMap& mR1, const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
     static bool configured = false;
     static int num_sms = 0;
-    constexpr int STAGE_BYTES = TC_A_BYTES + BN * 128;
+    constexpr int CL = MODE >= 2 ? 2 : 1;
+    // measured in one run (tools/bench_convgemm.py, conv 320->320 @ 28x72x128, pair mode): KC=1 1000, KC=2 1126 TFLOP/s;
+    // in mode 2 the doubled stage leaves only 2 stages for BN=160 and is slower.
+    constexpr int KC = (BN <= 160 && MODE == 3) ? 2 : 1;
+    constexpr int STAGE_BYTES = KC * (TC_A_BYTES + (MODE == 3 ? BN * 64 : BN * 128));
     if (!configured) {
-        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         int dev = 0;
         GCD_CUDA_CHECK(cudaGetDevice(&dev));
         GCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -515,7 +551,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GCD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CL>, mA, mB, mO, mO2, mR1, mR2, p));
+    GCD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, KC>, mA, mB, mO, mO2, mR1, mR2, p));
     g_launches++;
     return 0;
 }
@@ -582,14 +618,22 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     p.w_batched = op->w_batch_stride != 0;
     GCD_REQUIRE(!p.w_batched || TH == 1, "gcd_tc_run: batched weights need gemm tiling");
 
+    // Tile width: wide MMAs are markedly more efficient (measured per useful column, pair mode: BN=128 ~0.98, 160 ~1.14-1.26,
+    // 256 ~1.43 PFLOP/s; tools/bench_convgemm.py), and the last tile of a row is issued at its real width, so prefer 256
+    // unless that leaves a sliver; N = 320 (2 x 160) is the one shape where 160 wins.
     int BN;
-    if (op->N % 256 == 0) BN = 256;
+    if (op->N % 256 == 0 || op->N >= 384) BN = 256;
     else if (op->N % 160 == 0) BN = 160;
     else BN = 128;
+    static const int bn_env = [] { const char* e = getenv("GCD_TC_BN"); return e ? atoi(e) : 0; }();   // experiments only
+    if (bn_env == 128 || bn_env == 160 || bn_env == 256) { if (!e.geglu) BN = bn_env; }
     p.n_tiles = (op->N + BN - 1) / BN;
-    // 2-CTA clusters with multicast weights unless disabled (GCD_TC_CLUSTER=0), batched weights, or a single M-tile
-    static const int cluster_env = [] { const char* e = getenv("GCD_TC_CLUSTER"); return e ? atoi(e) : 2; }();
-    const int CL = (cluster_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? 2 : 1;
+    // MODE 3 (CTA pair, cta_group::2 MMA) unless overridden (GCD_TC_MODE=1|2|3), batched weights, or a single M-tile
+    static const int mode_env = [] { const char* e = getenv("GCD_TC_MODE"); return e ? atoi(e) : 3; }();
+    // short K loops are epilogue-bound: the looser coupling of mode 2 (multicast only) measured faster there
+    const int auto_mode = (p.ntaps * p.kchunks <= 10) ? 2 : 3;
+    const int MODE = (mode_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? (mode_env >= 3 ? auto_mode : 2) : 1;
+    const int CL = MODE >= 2 ? 2 : 1;
 
     p.bias = e.bias; p.rowvec = e.rowvec; p.rpv = e.rows_per_vec; p.ldv = e.ld_rowvec;
     p.has_r1 = e.res1 != nullptr; p.has_r2 = e.res2 != nullptr; p.r1f32 = e.res1_f32; p.r2f32 = e.res2_f32;
@@ -650,7 +694,10 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
         }
     }
     int rc;
-    switch (BN * 10 + CL) {
+    switch (BN * 10 + MODE) {
+        case 2563: rc = launch_tc<256, 3>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 1603: rc = launch_tc<160, 3>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 1283: rc = launch_tc<128, 3>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
         case 2562: rc = launch_tc<256, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
         case 1602: rc = launch_tc<160, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
         case 1282: rc = launch_tc<128, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
