@@ -14,10 +14,11 @@ extern std::atomic<int64_t> g_launches;
 template <bool IN_F32>
 __global__ void gn_stats_kernel(const void* __restrict__ in, int64_t rows, int C, int cpg, int rows_per_block,
                                 double* __restrict__ stats, int groups) {
-    __shared__ float s_sum[64], s_sq[64];
+    // Deterministic block reduction (no floating-point smem atomics: run-to-run bit differences in the statistics
+    // flipped 16-bit roundings downstream): per-thread fp32 partials -> smem [RY][C/2 pairs] -> one thread per group
+    // folds its pairs in a fixed order in fp64 -> one fp64 atomic per (block, group).
+    extern __shared__ float sm[];                      // [blockDim.y][C/2][2]
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    if (tid < 64) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
-    __syncthreads();
     const int img = blockIdx.y;
     const int c = threadIdx.x * 4;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -38,18 +39,19 @@ __global__ void gn_stats_kernel(const void* __restrict__ in, int64_t rows, int C
         sa += x0 + x1; qa += x0 * x0 + x1 * x1;
         sb += x2 + x3; qb += x2 * x2 + x3 * x3;
     }
-    const int ga = c / cpg, gb = (c + 2) / cpg;
-    if (ga == gb) {
-        atomicAdd(&s_sum[ga], sa + sb);
-        atomicAdd(&s_sq[ga], qa + qb);
-    } else {
-        atomicAdd(&s_sum[ga], sa); atomicAdd(&s_sq[ga], qa);
-        atomicAdd(&s_sum[gb], sb); atomicAdd(&s_sq[gb], qb);
-    }
+    const int npairs = C >> 1;
+    float* mine = sm + ((size_t)threadIdx.y * npairs + 2 * threadIdx.x) * 2;
+    mine[0] = sa; mine[1] = qa; mine[2] = sb; mine[3] = qb;
     __syncthreads();
     if (tid < groups) {
-        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 0], (double)s_sum[tid]);
-        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 1], (double)s_sq[tid]);
+        const int ppg = cpg >> 1;                      // channel pairs per group
+        double s = 0.0, q = 0.0;
+        for (int y = 0; y < (int)blockDim.y; y++) {
+            const float* row = sm + ((size_t)y * npairs + (size_t)tid * ppg) * 2;
+            for (int pp = 0; pp < ppg; pp++) { s += (double)row[2 * pp]; q += (double)row[2 * pp + 1]; }
+        }
+        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 0], s);
+        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 1], q);
     }
 }
 
@@ -124,10 +126,12 @@ extern "C" int gcd_groupnorm_stats(const void* in, int in_f32, int64_t n_img, in
     int rc = gn_geometry(n_img, rows, C, groups, &grid, &block, &rpb);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)block.y * (C / 2) * 2 * sizeof(float);
+    GCD_REQUIRE(smem <= 48 * 1024 && (int)(block.x * block.y) >= groups, "groupnorm_stats: unsupported geometry (C=%d)", C);
     if (in_f32)
-        gn_stats_kernel<true><<<grid, block, 0, st>>>(in, rows, C, C / groups, rpb, stats, groups);
+        gn_stats_kernel<true><<<grid, block, smem, st>>>(in, rows, C, C / groups, rpb, stats, groups);
     else
-        gn_stats_kernel<false><<<grid, block, 0, st>>>(in, rows, C, C / groups, rpb, stats, groups);
+        gn_stats_kernel<false><<<grid, block, smem, st>>>(in, rows, C, C / groups, rpb, stats, groups);
     GCD_CUDA_CHECK(cudaGetLastError());
     g_launches++;
     return 0;

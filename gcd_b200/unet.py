@@ -78,6 +78,7 @@ class UNetEngine:
         self.w = {}
         self._ca_cache = None
         self._pe_cache = {}
+        self.debug = None          # set to a list to record every layer's output (tools/bisect_batch.py)
         self._pack(state)
 
     # ------------------------------------------------------------------------------------------------ weight packing
@@ -391,6 +392,8 @@ class UNetEngine:
                     o = pool.get(f"{tag}{bi}u", (n * hH * hW, cout), torch.float32)
                     ops.conv2d_3x3(xu.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(o, bias=W[p + ".b"]))
                     h, hC, hst = o, cout, None      # consumed by a channel concat, not by a GroupNorm
+                if self.debug is not None:
+                    self.debug.append((p, kind, h.detach().clone()))
             return h, hH, hW, hC, hst
 
         hst = None

@@ -102,3 +102,29 @@ def test_decoder_vs_reference(tag):
     e = relerr(out, gold["decoded"])
     print(f"vae[{tag}] rel-L2 vs reference golden: {e:.3e}")
     assert e < TOL_DECODE
+
+
+def test_sampler_50_steps_scale_2p5_fused_equals_generic():
+    """Config 4 of BASELINE.json (50 steps, guider max scale 2.5) on the tiny network: fused == generic control flow."""
+    from gcd_b200 import sampling, spec
+    from gcd_b200.unet import VideoUNet
+    from oracle import weights
+    cfg = spec.UNET_TINY
+    net = VideoUNet(**spec.unet_ctor_kwargs(cfg))
+    net.load_state_dict(weights.seeded_state(spec.unet_param_shapes(cfg), seed=0))
+    net = net.cuda()
+    T = 2
+    den = sampling.Denoiser({"target": "gcd_b200.sampling.VScalingWithEDMcNoise"})
+    model = sampling.OpenAIWrapper(net)
+    sampler = sampling.EulerEDMSampler(
+        {"target": "gcd_b200.sampling.EDMDiscretization", "params": {"sigma_max": 700.0}}, num_steps=50,
+        guider_config={"target": "gcd_b200.sampling.LinearPredictionGuider", "params": {"num_frames": T, "max_scale": 2.5}},
+        device="cuda")
+    x, c, uc, ioi = weights.seeded_inputs(cfg, 1, T, 8, 8)
+    cuda = lambda d: {k: v.cuda() for k, v in d.items()}
+    extra = dict(image_only_indicator=torch.zeros(2, T).cuda(), num_video_frames=T)
+    opaque = lambda inp, sig, cc: den(model, inp, sig, cc, **extra)
+    a = sampler(opaque, x.clone().cuda(), cond=cuda(c), uc=cuda(uc))
+    b = sampler(sampling.FusedDenoiser(den, model, **extra), x.clone().cuda(), cond=cuda(c), uc=cuda(uc))
+    assert sampler.last_path == "fused" and torch.isfinite(a).all()
+    assert relerr(b, a) < 1e-2
