@@ -267,9 +267,10 @@ class EulerEDMSampler:
         c_noise_dev = c_noise.to(dev)
         x_cl = eng.pool.get("x_cl", (2 * BT, H, W, 64), eng.AD)
         t_in = eng.pool.get("t_in", (2 * BT,), torch.float32)
+        ca = eng.cross_attn_vectors(ctx, T)          # conditioning is constant over the steps: computed once per sample
         for i in range(sig.numel() - 1):
             ops.sampler_prep(x, ucc, cc, BT, H, W, host[3][i], x_cl)
             t_in.copy_(c_noise_dev[i].expand(2 * BT))
-            res = eng.forward_cl(x_cl, 2 * BT, H, W, t_in, ctx, y, T)
+            res = eng.forward_cl(x_cl, 2 * BT, H, W, t_in, ctx, y, T, ca=ca)
             ops.sampler_update(x, res, res.stride(0), BT, T, H, W, host[2][i], host[1][i], host[0][i], host[4][i], scale)
         return x

@@ -76,7 +76,6 @@ class UNetEngine:
         self.pool = BufferPool(self.device)
         self.plan = spec.unet_plan(cfg)
         self.w = {}
-        self._ca_cache = None
         self._pe_cache = {}
         self.debug = None          # set to a list to record every layer's output (tools/bisect_batch.py)
         self._pack(state)
@@ -211,12 +210,11 @@ class UNetEngine:
             self._pe_cache[key] = pe
         return self._pe_cache[key]
 
-    def _cross_attn_vectors(self, context, T):
+    def cross_attn_vectors(self, context, T):
         """len-1 cross attention == to_out(to_v(ctx)) (+bias): per frame for the spatial blocks, per clip
-        (context[::T], video_attention.py:249-253) for the temporal blocks. Cached on the context tensor."""
-        key = (context.data_ptr(), context._version, tuple(context.shape), T)
-        if self._ca_cache is not None and self._ca_cache[0] == key:
-            return self._ca_cache[1]
+        (context[::T], video_attention.py:249-253) for the temporal blocks. Step-invariant: the fused sampler computes
+        it once per sample and passes it to every step; a plain forward() recomputes it (no pointer-keyed caching —
+        a recycled allocation with new contents must never hit a stale entry)."""
         if context.dim() != 3 or context.shape[1] != 1:
             raise NotImplementedError(
                 f"gcd_b200.VideoUNet supports the GCD conditioning layout context=[BT,1,D] only, got {tuple(context.shape)}")
@@ -234,7 +232,6 @@ class UNetEngine:
                     o = torch.empty(c.shape[0], cout, device=self.device, dtype=torch.float32)
                     ops.linear(v, self.w[blk + ".attn2.out.w"], ops.make_ep(o, bias=self.w[blk + ".attn2.out.b"]))
                     vecs[blk] = o
-        self._ca_cache = (key, vecs)
         return vecs
 
     # ------------------------------------------------------------------------------------------------ blocks
@@ -349,14 +346,15 @@ class UNetEngine:
         ops.linear(es, W["emb_all.w"], ops.make_ep(emb_all, bias=W["emb_all.b"]))
         return emb_all
 
-    def forward_cl(self, x_cl, n, H, Wd, timesteps, context, y, T):
+    def forward_cl(self, x_cl, n, H, Wd, timesteps, context, y, T, ca=None):
         """x_cl: act channels-last [n, H, W, 64] (first in_channels used). Returns float32 [n*H*W, 16]-strided buffer
         whose first out_channels columns hold the result (channels-last)."""
         cfg, W, pool, AD = self.cfg, self.w, self.pool, self.AD
         assert n % T == 0
         B = n // T
         emb_all = self.embed(timesteps, y)
-        ca = self._cross_attn_vectors(context, T)
+        if ca is None:
+            ca = self.cross_attn_vectors(context, T)
         inp, mid, out = self.plan
         hs = []
         h, hH, hW, hC = None, H, Wd, None
