@@ -176,7 +176,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=1200))   # ranks build 1.5 B seeded weights on shared host cores first
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
     unet_cfg, vae_cfg = getattr(spec, wl["unet"]), spec.VAE_DECODER
