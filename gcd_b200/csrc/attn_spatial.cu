@@ -31,9 +31,6 @@ constexpr int TM_S = 0, TM_O = 128, TM_Q = 192;   // TMEM columns: S[2] (P_j ali
 constexpr int X_BYTES = 2 * 2 * BQ * 4;     // row max / row sum exchange between the two threads of a row [parity][half][row]
 constexpr int SMEM = KV_STAGES * 2 * KV_BYTES + X_BYTES + 1024 + 256;
 constexpr float RESCALE_TAU = 8.0f;          // log2 units
-#ifndef GCD_FA_EMU_EVERY
-#define GCD_FA_EMU_EVERY 0                   // default EMU: 0 = all exponentials on MUFU; n = every n-th pair on the FMA pipe
-#endif
 
 struct Params {
     int tokens, heads, nblk;
@@ -341,18 +338,19 @@ attn_kernel(const __grid_constant__ CUtensorMap mapKV, const Params p) {
 extern "C" int gcd_attention_spatial(const void* qkv, int frames, int tokens, int heads, void* out, void* stream) {
     GCD_REQUIRE(qkv && out && frames > 0 && tokens > 0 && heads > 0, "attention_spatial: bad arguments");
     GCD_REQUIRE(frames <= 65535 && heads <= 65535, "attention_spatial: grid too large");
-    static int emu = -1, split = 2;
-    if (emu < 0) {
+    static int emu_env = -2, split = 1;
+    if (emu_env == -2) {
 #define FA_CFG(E, S) GCD_CUDA_CHECK(cudaFuncSetAttribute(fa::attn_kernel<E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM))
-        FA_CFG(0, 1); FA_CFG(4, 1); FA_CFG(0, 2); FA_CFG(4, 2); FA_CFG(2, 2);
+        FA_CFG(0, 1); FA_CFG(4, 1); FA_CFG(0, 2); FA_CFG(4, 2);
 #undef FA_CFG
-        const char* e = getenv("GCD_FA_EMU");            // experiments: share of exponentials on the FMA pipe: 0, 4 (25 %), 2 (50 %)
-        const char* sp = getenv("GCD_FA_SPLIT");         // experiments: threads per query row (1 or 2)
-        split = sp ? atoi(sp) : 1;                    // 2 measured 10 % slower (exchange barrier, more instructions)
-        if (split != 2) split = 1;
-        emu = e ? atoi(e) : GCD_FA_EMU_EVERY;
-        if (emu != 0 && emu != 4 && !(emu == 2 && split == 2)) emu = 0;
+        const char* e = getenv("GCD_FA_EMU");            // experiments: share of exponentials on the FMA pipe: 0 or 4 (25 %)
+        const char* sp = getenv("GCD_FA_SPLIT");         // experiments: threads per query row; 2 measured 10 % slower
+        split = (sp && atoi(sp) == 2) ? 2 : 1;
+        emu_env = e ? (atoi(e) == 4 ? 4 : 0) : -1;
     }
+    // measured (tools/bench_attn.py): moving every 4th exponential pair to the FMA pipe gains ~2.5 % on the long-sequence level
+    // (9216 tokens) and loses ~1 % on the short ones
+    const int emu = emu_env >= 0 ? emu_env : (tokens >= 4096 ? 4 : 0);
     const int C = heads * 64;
     CUtensorMap mKV;
     uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)tokens, (uint64_t)frames};
@@ -366,9 +364,7 @@ extern "C" int gcd_attention_spatial(const void* qkv, int frames, int tokens, in
     cudaStream_t st = (cudaStream_t)stream;
 #define FA_GO(E, S) fa::attn_kernel<E, S><<<grid, 128 + 128 * S, fa::SMEM, st>>>(mKV, p)
     if (split == 1) { if (emu == 4) FA_GO(4, 1); else FA_GO(0, 1); }
-    else if (emu == 4) FA_GO(4, 2);
-    else if (emu == 2) FA_GO(2, 2);
-    else FA_GO(0, 2);
+    else { if (emu == 4) FA_GO(4, 2); else FA_GO(0, 2); }
 #undef FA_GO
     GCD_CUDA_CHECK(cudaGetLastError());
     g_launches++;
