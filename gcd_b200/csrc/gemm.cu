@@ -107,6 +107,7 @@ struct TcParams {
     int of32, geglu, act;
     double* gn_stats;           // fused GroupNorm statistics of the output (nullptr: off)
     int gn_cpg, gn_groups;
+    int gn_acc;                 // 1: accumulate the statistics per CTA in smem across tiles, flush when the image changes
     long long gn_rpi;
 };
 
@@ -171,7 +172,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint8_t* sR1 = sO + 2 * p.obufs * OT;                   // [2] residual 1 (if any)
     uint8_t* sR2 = sR1 + 2 * RT1;                           // [2] residual 2 (if any)
     float* sBias = reinterpret_cast<float*>(sR2 + 2 * RT2); // [2][256] bias slice of the current tile, per warpgroup
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 512);
+    float* sStat = sBias + 512;             // [8 epilogue warps][32 groups][sum, sum of squares] (gn_acc only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (p.gn_acc ? 512 : 0));
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + 8;            // [STAGES]  (STAGES <= 8)
     uint64_t* tfull = bars + 16;           // [2]
@@ -335,6 +337,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
         uint32_t ci = 0, rc = 0;                    // spans / residual chunks processed by this warpgroup
         int it = 0;
+        // gn_acc: many consecutive tiles of this CTA lie in the same image (VAE: 14 frames or ONE clip over 64 512 tiles),
+        // where per-tile global fp64 atomics serialise on 64 addresses in L2 (measured: 2.7 -> 5-6 ms per full-resolution
+        // conv). Each epilogue warp then sums into its own shared-memory table (plain adds in a fixed order: deterministic)
+        // and the CTA flushes the eight tables with fp64 atomics when the image changes.
+        int cur_img = -1;
+        float* myStat = sStat + (warp - 4) * 64;
+        auto flush_stats = [&]() {
+            named_bar_sync(3, 256);                                // both warpgroups' adds for cur_img are done
+            if (g == 0 && (threadIdx.x & 127) < 64) {
+                const int i = threadIdx.x & 127;
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) { v += (double)sStat[w * 64 + i]; sStat[w * 64 + i] = 0.f; }
+                if (v != 0.0) atomicAdd(p.gn_stats + (int64_t)cur_img * p.gn_groups * 2 + i, v);
+            }
+            named_bar_sync(3, 256);
+        };
+        if (p.gn_acc) {
+            myStat[lane] = 0.f; myStat[lane + 32] = 0.f;
+            named_bar_sync(3, 256);
+        }
         for (int tile = tile0; tile < total; tile += tile_step, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
@@ -344,6 +367,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int ty = (mt / p.ntx) % p.nty;
             const int tz = mt / (p.ntx * p.nty);
             const int n0 = nt * BN;
+            if (p.gn_acc && mt < m_tiles) {
+                const int64_t row0 = ((int64_t)(tz * TN) * p.Yo + ty * TH) * p.Xo + tx * TW;
+                const int img = (int)(row0 / p.gn_rpi);
+                if (img != cur_img) {
+                    if (cur_img >= 0) flush_stats();
+                    cur_img = img;
+                }
+            }
             const float* rv = nullptr;
             if (p.rowvec) {
                 const int x = tx * TW + (r & (TW - 1));
@@ -461,6 +492,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const int col = n0 + s0 + cc + lane;
                         float s1 = 0.f, s2 = 0.f;
                         if (col < p.N) {
+                            // (fully unrolling this loop with independent accumulators measured 1.6x SLOWER: the epilogue's
+                            // instruction footprint is what the 32 KB instruction cache tolerates, see profiles/r1_notes.md §1)
 #pragma unroll 4
                             for (int rr = 0; rr < 32; rr++) {
                                 const int row = q * 32 + rr;
@@ -479,10 +512,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                         const bool last = (gl == p.gn_cpg - 1) || lane == 31 || col == p.N - 1;
                         if (last && col < p.N) {
-                            const int64_t row0 = ((int64_t)(tz * TN) * p.Yo + ty * TH) * p.Xo + tx * TW;
-                            double* dst = p.gn_stats + ((row0 / p.gn_rpi) * p.gn_groups + col / p.gn_cpg) * 2;
-                            atomicAdd(dst, (double)s1);
-                            atomicAdd(dst + 1, (double)s2);
+                            if (p.gn_acc) {
+                                myStat[(col / p.gn_cpg) * 2] += s1;        // one lane per group: no conflicts inside the warp
+                                myStat[(col / p.gn_cpg) * 2 + 1] += s2;
+                            } else {
+                                const int64_t row0 = ((int64_t)(tz * TN) * p.Yo + ty * TH) * p.Xo + tx * TW;
+                                double* dst = p.gn_stats + ((row0 / p.gn_rpi) * p.gn_groups + col / p.gn_cpg) * 2;
+                                atomicAdd(dst, (double)s1);
+                                atomicAdd(dst + 1, (double)s2);
+                            }
                         }
                     }
                 }
@@ -490,6 +528,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_before();
             if (PAIR) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
         }
+        if (p.gn_acc && cur_img >= 0) flush_stats();
         if (leader) bulk_wait_read<0>();
     }
 
@@ -529,10 +568,27 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     const int RT = (p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0) + (p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0);
     const int kiters = p.ntaps * p.kchunks;
     // short K loop => the epilogue is the critical path: double-buffer its staging tiles if >= 3 pipeline stages remain
-    p.obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * RT) - 2304) / STAGE_BYTES >= 3) ? 2 : 1;
-    const int epi = 2 * p.obufs * OT + 2 * RT + 2048 /*bias*/;
-    int stages = (TC_SMEM_MAX - epi - 256) / STAGE_BYTES;
-    if (stages > 8) stages = 8;
+    auto plan = [&](int fixed, int& obufs, int& stages) {
+        obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
+        stages = (TC_SMEM_MAX - (2 * obufs * OT + 2 * RT + fixed) - 256) / STAGE_BYTES;
+        if (stages > 8) stages = 8;
+    };
+    int fixed = 2048 /*bias*/, stages;
+    plan(fixed, p.obufs, stages);
+    if (p.gn_stats) {
+        // consecutive tiles of a CTA are num_sms M-tiles apart: accumulate per CTA when an image spans many such strides ...
+        const int64_t rows = (int64_t)p.Xo * p.Yo * p.Zo;
+        const int64_t n_img = (rows + p.gn_rpi - 1) / p.gn_rpi;
+        int ob2, st2;
+        plan(fixed + 2048, ob2, st2);
+        // ... unless the 2 KB of tables would leave fewer than 4 pipeline stages (then keep the direct global atomics)
+        if (p.gn_groups == 32 && (int64_t)p.ntx * p.nty * p.ntz / n_img >= 4 * (int64_t)num_sms && ob2 == p.obufs && (st2 == stages || st2 >= 4)) {
+            p.gn_acc = 1;
+            stages = st2;
+            fixed += 2048;
+        }
+    }
+    const int epi = 2 * p.obufs * OT + 2 * RT + fixed;
     GCD_REQUIRE(stages >= 2, "tc_gemm: not enough shared memory for the pipeline (BN=%d)", BN);
     p.stages = stages;
     const int smem = stages * STAGE_BYTES + epi + 256;

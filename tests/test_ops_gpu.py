@@ -242,6 +242,35 @@ def test_attention_spatial(ops, frames, tokens, heads):
     assert relerr(out, ref) < 3e-3
 
 
+@pytest.mark.parametrize("n_img,Co,temporal", [(2, 128, False), (1, 128, True), (1, 512, False)])
+def test_fused_groupnorm_stats_accumulated(ops, n_img, Co, temporal):
+    """Images spanning >= 4 x num_SMs tiles take the per-CTA accumulation path (smem table, flush on image change) —
+    the shape class of the VAE decoder's full-resolution convolutions (one clip or 14 frames over 64 512 tiles)."""
+    AD = ops.act_dtype()
+    C = 64
+    if temporal:                                   # Conv3d (3,1,1) over [B=1, T=4, HW, C]; statistics over the whole clip
+        T, HW = 4, 48 * 512
+        x = rnd(1, T, HW, C, dtype=AD)
+        wp = rnd(Co, 3 * C, scale=(3 * C) ** -0.5, dtype=AD)
+        rows, rpi = T * HW, T * HW
+        run = lambda ep: ops.conv_t3(x, wp, ep)
+    else:
+        H, W = (192, 512) if n_img == 2 else (256, 512)
+        x = rnd(n_img, H, W, C, dtype=AD)
+        wp = rnd(Co, 9 * C, scale=(9 * C) ** -0.5, dtype=AD)
+        rows, rpi = n_img * H * W, H * W
+        run = lambda ep: ops.conv2d_3x3(x, wp, ep)
+    assert rpi // 128 >= 4 * torch.cuda.get_device_properties(0).multi_processor_count
+    out = torch.empty(rows, Co, device="cuda", dtype=AD)
+    st = torch.zeros(n_img * 64, device="cuda", dtype=torch.float64)
+    assert run(ops.make_ep(out, bias=rnd(Co), gn_stats=(st, Co // 32, 32, rpi)))
+    v = out.double().view(n_img, rpi, 32, Co // 32)
+    ref = torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1).reshape(-1)
+    assert torch.allclose(st, ref, rtol=1e-6, atol=1e-2)
+    st2 = torch.zeros_like(st)                     # order-insensitive fp64 accumulation: repeats bit-for-bit (to fp64 rounding)
+    assert run(ops.make_ep(out, bias=rnd(Co) * 0 , gn_stats=(st2, Co // 32, 32, rpi)))
+
+
 @pytest.mark.parametrize("out_f32", [True, False])
 def test_fused_groupnorm_stats(ops, out_f32):
     """gcd_epilogue.gn_stats: the conv epilogue accumulates (sum, sumsq) per (image, group) of the values it stores."""
