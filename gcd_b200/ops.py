@@ -182,6 +182,20 @@ def conv2d_3x3(x, w, ep, stride=1):
                   in_mul=stride)
 
 
+TAPS_3x3_PAD01 = [(kx, ky, 0) for ky in range(3) for kx in range(3)]
+
+
+def conv2d_3x3_down_pad01(x, w, ep):
+    """VAE-encoder Downsample (diffusionmodules/model.py:74-91): F.pad(x, (0, 1, 0, 1)) then a 3x3 conv with stride 2 and no
+    padding => output (ho, wo) reads input rows 2*ho..2*ho+2, cols 2*wo..2*wo+2; the right/bottom zero column/row is the
+    TMA out-of-bounds fill. x: act [n, H, W, C] channels-last; w: act [Cout, 9*C] packed (ky, kx, c)."""
+    n, H, W_, C = x.shape
+    assert x.is_contiguous() and w.shape[1] == 9 * C
+    Ho, Wo = (H - 2) // 2 + 1, (W_ - 2) // 2 + 1
+    return tc_run(x, C, (W_, H, n), (C, W_ * C, H * W_ * C), (Wo, Ho, n), TAPS_3x3_PAD01, w, w.stride(0), w.shape[0], ep,
+                  in_mul=2)
+
+
 def conv_t3(x, w, ep):
     """x: act [B, T, HW, C] contiguous; w: act [Cout, 3*C] packed (kt, c). Conv3d kernel (3,1,1), padding (1,0,0)."""
     B, T, HW, C = x.shape

@@ -6,7 +6,7 @@ import torch
 
 from . import sampling, spec
 from .unet import VideoUNet
-from .vae import VideoDecoder
+from .vae import Encoder, VideoDecoder
 
 
 class GCDHotPath:
@@ -33,6 +33,29 @@ class GCDHotPath:
         self.unet.to(self.device)
         self.decoder.to(self.device)
         return self
+
+    def load_cond_encoder(self, encoder_state, quant_weight, quant_bias, enc_cfg=None):
+        """Optional front-end: the AutoencoderKLModeOnly that VideoPredictionEmbedderWithEncoder
+        wraps (configs/infer_kubric.yaml:69-96). `encoder_state` uses the reference keys below `...encoder.encoder.`."""
+        self.enc_cfg = dict(enc_cfg or spec.VAE_ENCODER)
+        self.encoder = Encoder(**spec.encoder_ctor_kwargs(self.enc_cfg))
+        self.encoder.load_state_dict(encoder_state, strict=True)
+        self.encoder.to(self.device)
+        self.quant = (quant_weight.to(self.device, torch.float32), quant_bias.to(self.device, torch.float32))
+        return self
+
+    @torch.no_grad()
+    def encode_cond_frames(self, frames, n_cond_frames=1, n_copies=1):
+        """VideoPredictionEmbedderWithEncoder.forward without noise augmentation (encoders/modules.py:1090-1109; the shipped
+        configs set no sigma_sampler and n_cond_frames = n_copies = 1, infer_kubric.yaml:75-76): frames [B*T,3,H,W] in
+        [-1,1] -> scale_factor * mode(encode), then "(b t) c h w -> b () (t c) h w" repeated n_copies times. The result is
+        the `concat` conditioning the UNet wrapper appends to the noisy latents (wrappers.py:24)."""
+        z = self.encoder.encode_mode(frames.to(self.device, non_blocking=True), self.quant[0], self.quant[1], self.scale_factor)
+        if n_cond_frames == 1 and n_copies == 1:
+            return z
+        bt, c, h, w = z.shape
+        z = z.view(bt // n_cond_frames, 1, n_cond_frames * c, h, w)
+        return z.expand(-1, n_copies, -1, -1, -1).reshape(-1, n_cond_frames * c, h, w)
 
     @torch.no_grad()
     def sample_latents(self, noise, c, uc, num_steps=None):

@@ -14,6 +14,9 @@ UNET_PARDOM = dict(UNET_KUBRIC, aux_emb_dim=0)                       # configs/i
 UNET_TINY = dict(UNET_KUBRIC, model_channels=64)                     # reduced width for fast tests
 VAE_DECODER = dict(ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=4)  # infer_kubric.yaml:151-164
 VAE_TINY = dict(VAE_DECODER, ch=64)
+# conditioning-frame encoder (AutoencoderKLModeOnly.encoder, infer_kubric.yaml:78-96) — SURVEY.md §8(f) rank 1
+VAE_ENCODER = dict(ch=128, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=4, in_channels=3, double_z=True)
+VAE_ENCODER_TINY = dict(VAE_ENCODER, ch=64)
 
 
 def unet_plan(cfg):
@@ -184,6 +187,55 @@ def decoder_param_shapes(cfg):
             _wb(d, "conv_out", cout, cin, 3, 3)
             _wb(d, "conv_out.time_mix_conv", cout, cout, 3, 1, 1)
     return d
+
+
+def encoder_plan(cfg):
+    """Encoder.__init__/forward (diffusionmodules/model.py:487-601): (kind, prefix, cin, cout) in execution order."""
+    ch, mult, nrb = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"]
+    plan = [("conv_in", "conv_in", cfg["in_channels"], ch)]
+    block_in = ch
+    for lvl in range(len(mult)):
+        block_out = ch * mult[lvl]
+        for i in range(nrb):
+            plan.append(("res", f"down.{lvl}.block.{i}", block_in, block_out))
+            block_in = block_out
+        if lvl != len(mult) - 1:
+            plan.append(("down", f"down.{lvl}.downsample", block_in, block_in))
+    plan += [("res", "mid.block_1", block_in, block_in), ("attn", "mid.attn_1", block_in, block_in),
+             ("res", "mid.block_2", block_in, block_in),
+             ("out", "conv_out", block_in, (2 if cfg.get("double_z", True) else 1) * cfg["z_channels"])]
+    return plan
+
+
+def encoder_param_shapes(cfg):
+    d = OrderedDict()
+    for kind, p, cin, cout in encoder_plan(cfg):
+        if kind == "conv_in":
+            _wb(d, p, cout, cin, 3, 3)
+        elif kind == "res":
+            _wb(d, p + ".norm1", cin)
+            _wb(d, p + ".conv1", cout, cin, 3, 3)
+            _wb(d, p + ".norm2", cout)
+            _wb(d, p + ".conv2", cout, cout, 3, 3)
+            if cin != cout:
+                _wb(d, p + ".nin_shortcut", cout, cin, 1, 1)
+        elif kind == "attn":
+            _wb(d, p + ".norm", cin)
+            for n in ("q", "k", "v", "proj_out"):
+                _wb(d, f"{p}.{n}", cin, cin, 1, 1)
+        elif kind == "down":
+            _wb(d, p + ".conv", cout, cin, 3, 3)
+        elif kind == "out":
+            _wb(d, "norm_out", cin)
+            _wb(d, "conv_out", cout, cin, 3, 3)
+    return d
+
+
+def encoder_ctor_kwargs(cfg):
+    """Constructor kwargs of the VAE Encoder as in configs/infer_kubric.yaml:83-94 (ddconfig)."""
+    return dict(attn_type="vanilla", double_z=cfg.get("double_z", True), z_channels=cfg["z_channels"], resolution=256,
+                in_channels=cfg["in_channels"], out_ch=3, ch=cfg["ch"], ch_mult=cfg["ch_mult"],
+                num_res_blocks=cfg["num_res_blocks"], attn_resolutions=[], dropout=0.0)
 
 
 def unet_ctor_kwargs(cfg):

@@ -182,6 +182,176 @@ class DecoderEngine:
         return out_nchw
 
 
+class EncoderEngine(DecoderEngine):
+    """VAE Encoder of the conditioning frames (diffusionmodules/model.py:487-601): the same
+    channels-last fp32-residual design and the same kernels as the decoder, plus the stride-2 (0,1,0,1)-padded Downsample conv.
+
+    `post=(Wq [co, 2z], bq [co], scale)` folds a following 1x1 conv and scale into conv_out — exact algebra:
+    scale * (Wq (W_out * h + b_out) + bq) = (scale Wq W_out) * h + scale (Wq b_out + bq). AutoencoderKLModeOnly
+    (autoencoder.py:493-513,627-640) is quant_conv followed by "take the mean half", i.e. post = (Wq[:z], bq[:z], scale_factor).
+    """
+
+    def __init__(self, cfg, state, device, post=None):
+        self.cfg, self.device, self.AD = cfg, torch.device(device), ops.act_dtype()
+        self.pool = BufferPool(self.device)
+        self.plan = spec.encoder_plan(cfg)
+        self.w, self.alpha = {}, {}
+        self._pack_encoder(state, post)
+
+    def _pack_encoder(self, sd, post):
+        dev, AD, W = self.device, self.AD, self.w
+        g = lambda k: sd[k].detach().to(dev, torch.float32)
+
+        def conv3(name, w, b, cin_pad=None):
+            if cin_pad is not None and cin_pad != w.shape[1]:
+                w = torch.cat([w, w.new_zeros(w.shape[0], cin_pad - w.shape[1], 3, 3)], 1)
+            W[name + ".w"] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(AD).contiguous()
+            W[name + ".b"] = b.contiguous()
+
+        def norm(name, key):
+            W[name + ".g"], W[name + ".b"] = g(key + ".weight").contiguous(), g(key + ".bias").contiguous()
+
+        for kind, p, cin, cout in self.plan:
+            if kind == "conv_in":
+                conv3(p, g(p + ".weight"), g(p + ".bias"), cin_pad=64)
+            elif kind == "res":
+                norm(p + ".n1", p + ".norm1"); conv3(p + ".c1", g(p + ".conv1.weight"), g(p + ".conv1.bias"))
+                norm(p + ".n2", p + ".norm2"); conv3(p + ".c2", g(p + ".conv2.weight"), g(p + ".conv2.bias"))
+                if cin != cout:
+                    W[p + ".skip.w"] = g(p + ".nin_shortcut.weight")[:, :, 0, 0].to(AD).contiguous()
+                    W[p + ".skip.b"] = g(p + ".nin_shortcut.bias").contiguous()
+            elif kind == "attn":
+                norm(p + ".norm", p + ".norm")
+                for n in ("q", "k", "v", "proj_out"):
+                    W[f"{p}.{n}.w"] = g(f"{p}.{n}.weight")[:, :, 0, 0].to(AD).contiguous()
+                    W[f"{p}.{n}.b"] = g(f"{p}.{n}.bias").contiguous()
+            elif kind == "down":
+                conv3(p, g(p + ".conv.weight"), g(p + ".conv.bias"))
+            elif kind == "out":
+                norm("norm_out", "norm_out")
+                w, b = g("conv_out.weight"), g("conv_out.bias")
+                if post is not None:
+                    wq, bq, scale = post
+                    wq, bq = wq.detach().to(dev, torch.float32).reshape(wq.shape[0], -1), bq.detach().to(dev, torch.float32)
+                    w = float(scale) * torch.einsum("oc,cikl->oikl", wq, w)
+                    b = float(scale) * (wq @ b + bq)
+                self.out_ch = w.shape[0]
+                assert self.out_ch <= 16
+                conv3("conv_out", w, b)
+        self.weight_bytes = sum(t.numel() * t.element_size() for t in W.values())
+
+    def _res2d(self, p, x, cin, cout, n, H, Wd, tag, x_stats=None):
+        """ResnetBlock.forward with temb=None (model.py:127-151). Returns (x_out fp32, per-frame GroupNorm stats or None)."""
+        W, pool, AD = self.w, self.pool, self.AD
+        HW, rows = H * Wd, n * H * Wd
+        a = pool.get(f"a{cin}_{rows}", (rows, cin), AD)
+        self._gn(x, n, HW, cin, p + ".n1", 1e-6, True, a, stats=x_stats)
+        h1 = pool.get(f"h{cout}_{rows}", (rows, cout), AD)
+        st, req = self._stats_req(n, cout, HW)
+        ok = ops.conv2d_3x3(a.view(n, H, Wd, cin), W[p + ".c1.w"], ops.make_ep(h1, bias=W[p + ".c1.b"], gn_stats=req))
+        a2 = pool.get(f"a{cout}_{rows}", (rows, cout), AD)
+        self._gn(h1, n, HW, cout, p + ".n2", 1e-6, True, a2, stats=st if ok else None)
+        xs = pool.get(f"{tag}_{cout}_{rows}", (rows, cout), torch.float32)
+        if cin != cout:
+            xa = pool.get(f"xa{cin}_{rows}", (rows, cin), AD)
+            ops.cast_to_act(x, xa)
+            ops.linear(xa, W[p + ".skip.w"], ops.make_ep(xs, bias=W[p + ".skip.b"]))
+            res = xs
+        else:
+            res = x
+        st, req = self._stats_req(n, cout, HW)
+        ok = ops.conv2d_3x3(a2.view(n, H, Wd, cout), W[p + ".c2.w"], ops.make_ep(xs, bias=W[p + ".c2.b"], res1=res, gn_stats=req))
+        return xs, (st if ok else None)
+
+    def forward_cl(self, x_cl, n, H, Wd, out_nchw):
+        """x_cl: act channels-last [n, H, W, 64] (image channels zero-padded); writes float32 NCHW [n, out_ch, H/8, W/8]."""
+        W, pool, AD = self.w, self.pool, self.AD
+        h, hH, hW, hst = None, H, Wd, None
+        for i, (kind, p, cin, cout) in enumerate(self.plan):
+            rows = n * hH * hW
+            if kind == "conv_in":
+                h = pool.get(f"s0_{cout}_{rows}", (rows, cout), torch.float32)
+                st, req = self._stats_req(n, cout, hH * hW)
+                ok = ops.conv2d_3x3(x_cl, W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"], gn_stats=req))
+                hst = st if ok else None
+            elif kind == "res":
+                h, hst = self._res2d(p, h, cin, cout, n, hH, hW, f"s{1 + i % 2}", x_stats=hst)
+            elif kind == "attn":
+                h = self._attn(p, h, cin, n, hH * hW, x_stats=hst)
+                hst = None
+            elif kind == "down":
+                assert hH % 2 == 0 and hW % 2 == 0, "Downsample expects even sizes (the reference pads (0,1,0,1) and floors)"
+                xa = pool.get(f"dn{cin}_{rows}", (rows, cin), AD)
+                ops.cast_to_act(h, xa)
+                h = pool.get(f"s0_{cout}_{rows // 4}", (rows // 4, cout), torch.float32)
+                st, req = self._stats_req(n, cout, (hH // 2) * (hW // 2))
+                ok = ops.conv2d_3x3_down_pad01(xa.view(n, hH, hW, cin), W[p + ".w"], ops.make_ep(h, bias=W[p + ".b"], gn_stats=req))
+                hH, hW = hH // 2, hW // 2
+                hst = st if ok else None
+            elif kind == "out":
+                a = pool.get(f"a{cin}_{rows}", (rows, cin), AD)
+                self._gn(h, n, hH * hW, cin, "norm_out", 1e-6, True, a, stats=hst)
+                o16 = pool.get(f"out16_{rows}", (rows, 16), torch.float32)
+                ops.conv2d_3x3(a.view(n, hH, hW, cin), W["conv_out.w"], ops.make_ep(o16[:, :self.out_ch], bias=W["conv_out.b"]))
+                ops.nhwc_to_nchw(o16, 16, n, self.out_ch, hH * hW, out_nchw)
+        return out_nchw
+
+
+class Encoder(nn.Module):
+    """Drop-in `target:` for sgm.modules.diffusionmodules.model.Encoder (ctor kwargs: infer_kubric.yaml:83-94); state-dict
+    keys equal the reference's (`...encoder.encoder.*`). forward(x [n, 3, H, W]) -> moments [n, 2*z_channels, H/8, W/8].
+    `encode_mode` is the fused AutoencoderKLModeOnly.encode + VideoPredictionEmbedderWithEncoder scale (modules.py:1100-1106)."""
+
+    def __init__(self, *, ch, out_ch=3, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions=(), dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution=256, z_channels, double_z=True, use_linear_attn=False,
+                 attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(f"gcd_b200.Encoder: unsupported option ({what}); only the GCD config is built")
+
+        need(len(attn_resolutions) == 0 and attn_type in ("vanilla", "vanilla-xformers") and not use_linear_attn, "attention")
+        need(resamp_with_conv and dropout == 0.0, "resamp_with_conv / dropout")
+        need(ch % 64 == 0 and in_channels <= 64 and (2 if double_z else 1) * z_channels <= 16, "channel counts")
+        self.cfg = dict(ch=ch, ch_mult=list(ch_mult), num_res_blocks=num_res_blocks, z_channels=z_channels,
+                        in_channels=in_channels, double_z=double_z)
+        register_param_tree(self, spec.encoder_param_shapes(self.cfg))
+        self._engines = {}
+
+    def engine(self, device, post=None, post_key=None):
+        key = (str(device), post_key, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        if key not in self._engines:
+            self._engines = {key: EncoderEngine(self.cfg, self.state_dict(), device, post=post)}
+        return self._engines[key]
+
+    def _run(self, x, eng):
+        if not x.is_cuda:
+            raise RuntimeError("gcd_b200.Encoder runs on CUDA (sm_100a) only; there is no CPU path")
+        n, c, H, W = x.shape
+        ndown = len(self.cfg["ch_mult"]) - 1
+        if c != self.cfg["in_channels"] or H % (1 << ndown) or W % (1 << ndown) or ((H >> ndown) * (W >> ndown)) % 8:
+            raise ValueError(f"Encoder input must be [n, {self.cfg['in_channels']}, H, W] with H, W multiples of {1 << ndown} "
+                             f"and (H/{1 << ndown})*(W/{1 << ndown}) a multiple of 8 (16-byte rows of the mid-attention scores)")
+        x_cl = eng.pool.get("x_cl", (n, H, W, 64), eng.AD)
+        ops.nchw_to_act_nhwc(x.to(torch.float32).contiguous(), n, c, H * W, 64, x_cl)
+        out = torch.empty(n, eng.out_ch, H >> ndown, W >> ndown, device=x.device, dtype=torch.float32)
+        eng.forward_cl(x_cl, n, H, W, out)
+        return out.to(x.dtype)
+
+    @torch.no_grad()
+    def forward(self, x):
+        return self._run(x, self.engine(x.device))
+
+    @torch.no_grad()
+    def encode_mode(self, x, quant_weight, quant_bias, scale_factor=1.0):
+        """scale_factor * mode(DiagonalGaussian(quant_conv(encoder(x)))) = the first z_channels of quant_conv's output."""
+        z = self.cfg["z_channels"]
+        post = (quant_weight[:z], quant_bias[:z], scale_factor)
+        pk = (quant_weight.data_ptr(), quant_weight._version, quant_bias.data_ptr(), quant_bias._version, float(scale_factor))
+        return self._run(x, self.engine(x.device, post=post, post_key=pk))
+
+
 def _reference_base():
     try:
         from sgm.modules.autoencoding.temporal_ae import VideoDecoder as Ref   # noqa: WPS433

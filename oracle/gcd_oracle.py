@@ -24,6 +24,7 @@ UNET_KUBRIC = dict(  # gcd-model/configs/infer_kubric.yaml:18-40
     aux_emb_dim=128)
 UNET_PARDOM = dict(UNET_KUBRIC, aux_emb_dim=0)  # gcd-model/configs/infer_pardom.yaml
 VAE_DECODER = dict(ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=4)  # infer_kubric.yaml:151-164
+VAE_ENCODER = dict(ch=128, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=4, in_channels=3, double_z=True)  # :83-94
 
 
 def unet_plan(cfg):
@@ -332,3 +333,40 @@ def decoder_forward(sd, cfg, z, timesteps):
 def decode_first_stage(sd, cfg, z, T, scale_factor=0.18215):
     """DiffusionEngine.decode_first_stage (models/diffusion.py:233-251), one chunk of T frames, fp32."""
     return decoder_forward(sd, cfg, z / scale_factor, T)
+
+
+# ---------------------------------------------------------------------------------------------------------- VAE encoder
+# SURVEY.md §8(f) rank 1: the conditioning-frame encoder that runs once per sample, immediately before the hot path.
+def vae_resblock2d(sd, p, x):
+    """model.ResnetBlock.forward with temb=None (diffusionmodules/model.py:127-151)."""
+    h = F.conv2d(F.silu(_gn(sd, p + ".norm1", x, 1e-6)), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+    h = F.conv2d(F.silu(_gn(sd, p + ".norm2", h, 1e-6)), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    if (p + ".nin_shortcut.weight") in sd:
+        x = F.conv2d(x, sd[p + ".nin_shortcut.weight"], sd[p + ".nin_shortcut.bias"])
+    return x + h
+
+
+def encoder_forward(sd, cfg, x):
+    """Encoder.forward (model.py:576-601); Downsample = pad (0,1,0,1) + 3x3 stride-2 conv without padding (model.py:84-88)."""
+    nres = len(cfg["ch_mult"])
+    h = F.conv2d(x, sd["conv_in.weight"], sd["conv_in.bias"], padding=1)
+    for lvl in range(nres):
+        for i in range(cfg["num_res_blocks"]):
+            h = vae_resblock2d(sd, f"down.{lvl}.block.{i}", h)
+        if lvl != nres - 1:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[f"down.{lvl}.downsample.conv.weight"],
+                         sd[f"down.{lvl}.downsample.conv.bias"], stride=2)
+    h = vae_resblock2d(sd, "mid.block_1", h)
+    h = vae_attn(sd, "mid.attn_1", h)
+    h = vae_resblock2d(sd, "mid.block_2", h)
+    h = F.silu(_gn(sd, "norm_out", h, 1e-6))
+    return F.conv2d(h, sd["conv_out.weight"], sd["conv_out.bias"], padding=1)
+
+
+def encode_cond_frames(sd, cfg, x, quant_weight, quant_bias, scale_factor=0.18215):
+    """AutoencodingEngineLegacy.encode (models/autoencoder.py:493-513): quant_conv(encoder(x)), regularised by
+    DiagonalGaussianRegularizer(sample=False) = the distribution's mode = the mean half of the channels
+    (distributions/distributions.py:25-28,71-72), then VideoPredictionEmbedderWithEncoder's `vid *= scale_factor`
+    (encoders/modules.py:1106)."""
+    moments = F.conv2d(encoder_forward(sd, cfg, x), quant_weight, quant_bias)
+    return moments[:, :cfg["z_channels"]] * scale_factor

@@ -94,6 +94,30 @@ def pin_decoder(tag, cfg, T, H, W):
                os.path.join(GOLD, f"vae_{tag}.pt"))
 
 
+def pin_encoder(tag, cfg, n, H, W):
+    """Reference Encoder + quant_conv + DiagonalGaussianDistribution.mode() (the pieces of AutoencoderKLModeOnly.encode that
+    import here; the LightningModule wrapper itself needs pytorch_lightning)."""
+    enc = ref_shim.build_ref_encoder(cfg)
+    shapes = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    json.dump({k: list(v) for k, v in shapes.items()}, open(os.path.join(GOLD, f"enc_{tag}_keys.json"), "w"))
+    sd = weights.seeded_state(shapes, seed=0)
+    enc.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(777)
+    x = torch.randn(n, cfg["in_channels"], H, W, generator=g).clamp_(-1, 1)
+    zc = cfg["z_channels"]
+    qw = torch.randn(2 * zc, 2 * zc, 1, 1, generator=g) * 0.4
+    qb = torch.randn(2 * zc, generator=g) * 0.1
+    from sgm.modules.distributions.distributions import DiagonalGaussianDistribution
+    moments = enc(x)
+    mode = DiagonalGaussianDistribution(torch.nn.functional.conv2d(moments, qw, qb)).mode() * 0.18215
+    e1 = maxrel(O.encoder_forward(sd, cfg, x), moments)
+    e2 = maxrel(O.encode_cond_frames(sd, cfg, x, qw, qb), mode)
+    print(f"[enc {tag}] oracle vs reference: moments {e1:.2e}, mode*scale {e2:.2e}")
+    assert e1 < 2e-5 and e2 < 2e-5, (e1, e2)
+    torch.save({"cfg": cfg, "n": n, "H": H, "W": W, "x": x, "quant_w": qw, "quant_b": qb, "moments": moments.clone(),
+                "mode_scaled": mode.clone()}, os.path.join(GOLD, f"enc_{tag}.pt"))
+
+
 def pin_closed_forms():
     """Known-answer values derivable from the source."""
     ref_shim.install()
@@ -120,7 +144,9 @@ if __name__ == "__main__":
     pin_closed_forms()
     pin_unet("tiny", UNET_TINY, B=1, T=3, H=16, W=24, steps=4)
     pin_decoder("tiny", VAE_TINY, T=3, H=8, W=8)
+    pin_encoder("tiny", dict(O.VAE_ENCODER, ch=64), n=2, H=64, W=96)
     if "--full" in sys.argv:
         pin_unet("kubric", O.UNET_KUBRIC, B=1, T=2, H=16, W=16, steps=2)
         pin_unet("pardom", O.UNET_PARDOM, B=1, T=2, H=8, W=8, steps=1)
         pin_decoder("full", O.VAE_DECODER, T=2, H=8, W=8)
+        pin_encoder("full", O.VAE_ENCODER, n=1, H=64, W=64)

@@ -64,3 +64,16 @@ def build_ref_decoder(cfg):
     with torch.device("meta"):
         dec = VideoDecoder(**kw)
     return dec.to_empty(device="cpu").eval()
+
+
+def build_ref_encoder(cfg):
+    """Reference VAE Encoder (diffusionmodules/model.py:487) on CPU with uninitialised storage."""
+    install()
+    import torch
+    from sgm.modules.diffusionmodules.model import Encoder
+    kw = dict(attn_type="vanilla", double_z=cfg.get("double_z", True), z_channels=cfg["z_channels"], resolution=256,
+              in_channels=cfg["in_channels"], out_ch=3, ch=cfg["ch"], ch_mult=cfg["ch_mult"],
+              num_res_blocks=cfg["num_res_blocks"], attn_resolutions=[], dropout=0.0)
+    with torch.device("meta"):
+        enc = Encoder(**kw)
+    return enc.to_empty(device="cpu").eval()

@@ -57,6 +57,16 @@ def test_oracle_decoder_vs_reference_golden():
     assert maxrel(out, gold["decoded"]) < 2e-5
 
 
+def test_oracle_encoder_vs_reference_golden():
+    """Encoder moments and the scaled mode (quant_conv + DiagonalGaussian.mode) vs the reference."""
+    gold = torch.load(os.path.join(GOLD, "enc_tiny.pt"))
+    cfg = gold["cfg"]
+    sd = synthetic.seeded_state(spec.encoder_param_shapes(cfg), seed=0)
+    with torch.no_grad():
+        assert maxrel(O.encoder_forward(sd, cfg, gold["x"]), gold["moments"]) < 2e-5
+        assert maxrel(O.encode_cond_frames(sd, cfg, gold["x"], gold["quant_w"], gold["quant_b"]), gold["mode_scaled"]) < 2e-5
+
+
 def test_len1_cross_attention_is_a_bias():
     """with one context token attn2(x, ctx) == to_out(to_v(ctx)), independent of x."""
     torch.manual_seed(0)
@@ -106,6 +116,17 @@ def test_unsupported_options_fail_loudly():
     net = VideoUNet(**kw)
     with pytest.raises(RuntimeError):   # no CPU fallback
         net(torch.zeros(2, 8, 8, 8), torch.zeros(2), context=torch.zeros(2, 1, 1024), y=torch.zeros(2, 896), num_video_frames=2)
+
+
+def test_encoder_rejects_unsupported_options_and_cpu_tensors():
+    from gcd_b200.vae import Encoder
+    kw = spec.encoder_ctor_kwargs(spec.VAE_ENCODER_TINY)
+    with pytest.raises(NotImplementedError):
+        Encoder(**dict(kw, attn_resolutions=[32]))
+    with pytest.raises(NotImplementedError):
+        Encoder(**dict(kw, resamp_with_conv=False))
+    with pytest.raises(RuntimeError):
+        Encoder(**kw)(torch.zeros(1, 3, 64, 64))
 
 
 def test_flop_model_matches_survey():

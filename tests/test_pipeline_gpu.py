@@ -104,6 +104,51 @@ def test_decoder_vs_reference(tag):
     assert e < TOL_DECODE
 
 
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_encoder_vs_reference(tag):
+    """VAE Encoder of the conditioning frames vs the reference Encoder's own outputs; the fused
+    quant_conv + mode + scale path vs reference quant_conv -> DiagonalGaussianDistribution.mode() * scale_factor."""
+    from gcd_b200 import spec
+    from gcd_b200.vae import Encoder
+    from oracle import weights
+    path = os.path.join(GOLD, f"enc_{tag}.pt")
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    gold = torch.load(path)
+    cfg = gold["cfg"]
+    enc = Encoder(**spec.encoder_ctor_kwargs(cfg))
+    enc.load_state_dict(weights.seeded_state(spec.encoder_param_shapes(cfg), seed=0), strict=True)
+    enc = enc.cuda()
+    out = enc(gold["x"].cuda())
+    assert out.shape == gold["moments"].shape
+    e1 = relerr(out, gold["moments"])
+    z = enc.encode_mode(gold["x"].cuda(), gold["quant_w"].cuda(), gold["quant_b"].cuda(), 0.18215)
+    assert z.shape == gold["mode_scaled"].shape
+    e2 = relerr(z, gold["mode_scaled"])
+    print(f"enc[{tag}] rel-L2 vs reference golden: moments {e1:.3e}, scaled mode {e2:.3e}")
+    assert e1 < TOL_DECODE and e2 < TOL_DECODE
+
+
+def test_encoder_live_oracle_ragged_shape():
+    """A non-square size whose level sizes (40x192, 20x96, 10x48, 5x24) leave ragged tiles, two frames."""
+    from gcd_b200 import spec
+    from gcd_b200.vae import Encoder
+    from oracle import gcd_oracle as O, weights
+    cfg = spec.VAE_ENCODER_TINY
+    sd = weights.seeded_state(spec.encoder_param_shapes(cfg), seed=3)
+    enc = Encoder(**spec.encoder_ctor_kwargs(cfg))
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda()
+    x = torch.randn(2, 3, 40, 192, generator=torch.Generator().manual_seed(5)).clamp_(-1, 1)
+    with torch.no_grad():
+        ref = O.encoder_forward(sd, cfg, x)
+    assert relerr(enc(x.cuda()), ref) < TOL_DECODE
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 3, 36, 64).cuda())          # not a multiple of 8
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 3, 40, 88).cuda())          # 5 x 11 mid-attention tokens: rows not 16-byte aligned
+
+
 def test_sampler_50_steps_scale_2p5_fused_equals_generic():
     """Config 4 of BASELINE.json (50 steps, guider max scale 2.5) on the tiny network: fused == generic control flow."""
     from gcd_b200 import sampling, spec

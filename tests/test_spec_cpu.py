@@ -16,6 +16,8 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
     ("unet_pardom_keys.json", lambda: spec.unet_param_shapes(spec.UNET_PARDOM)),
     ("vae_tiny_keys.json", lambda: spec.decoder_param_shapes(spec.VAE_TINY)),
     ("vae_full_keys.json", lambda: spec.decoder_param_shapes(spec.VAE_DECODER)),
+    ("enc_tiny_keys.json", lambda: spec.encoder_param_shapes(spec.VAE_ENCODER_TINY)),
+    ("enc_full_keys.json", lambda: spec.encoder_param_shapes(spec.VAE_ENCODER)),
 ])
 def test_param_tables_match_reference(fname, shapes):
     path = os.path.join(GOLD, fname)
@@ -35,6 +37,10 @@ def test_module_state_dict_keys():
     assert list(net.state_dict().keys()) == list(spec.unet_param_shapes(spec.UNET_TINY).keys())
     n = sum(p.numel() for p in net.parameters())
     assert n > 1e6
+    from gcd_b200.vae import Encoder
+    enc = Encoder(**spec.encoder_ctor_kwargs(spec.VAE_ENCODER))
+    assert list(enc.state_dict().keys()) == list(spec.encoder_param_shapes(spec.VAE_ENCODER).keys())
+    assert sum(p.numel() for p in enc.parameters()) == 34_163_592      # 34 M parameters
 
 
 def test_kubric_param_count():
