@@ -34,6 +34,11 @@ class GCDHotPath:
         self.decoder.to(self.device)
         return self
 
+    def set_cfg_parallel(self, group):
+        """Single-clip latency mode over a 2-rank group: see EulerEDMSampler.set_cfg_parallel."""
+        self.sampler.set_cfg_parallel(group)
+        return self
+
     def load_cond_encoder(self, encoder_state, quant_weight, quant_bias, enc_cfg=None):
         """Optional front-end: the AutoencoderKLModeOnly that VideoPredictionEmbedderWithEncoder
         wraps (configs/infer_kubric.yaml:69-96). `encoder_state` uses the reference keys below `...encoder.encoder.`."""

@@ -187,6 +187,18 @@ class EulerEDMSampler:
         self.verbose, self.device = verbose, device
         self.s_churn, self.s_tmin, self.s_tmax, self.s_noise = s_churn, s_tmin, s_tmax, s_noise
         self.last_path = None
+        self.cfg_group = None            # set_cfg_parallel(): 2-rank process group splitting the CFG pair of ONE clip
+
+    def set_cfg_parallel(self, group):
+        """Single-clip latency mode: the two ranks of `group` hold the same clip; rank 0 evaluates the
+        unconditional half of the classifier-free-guidance batch (guiders.py:89-100 puts `uc` first), rank 1 the conditional
+        half, and one all_gather of the network output per step (8 MB at 14x72x128) lets both apply the identical guided
+        Euler update. `None` switches back. Only the fused CUDA path honours it."""
+        if group is not None:
+            import torch.distributed as dist
+            if dist.get_world_size(group) != 2:
+                raise ValueError("cfg-parallel needs a process group of exactly 2 ranks (uc | c)")
+        self.cfg_group = group
 
     # ---- reference control flow -------------------------------------------------------------------------------
     def prepare_sampling_loop(self, x, cond, uc=None, num_steps=None):
@@ -267,10 +279,30 @@ class EulerEDMSampler:
         c_noise_dev = c_noise.to(dev)
         x_cl = eng.pool.get("x_cl", (2 * BT, H, W, 64), eng.AD)
         t_in = eng.pool.get("t_in", (2 * BT,), torch.float32)
+        if self.cfg_group is not None:
+            return self._run_fused_cfg_parallel(eng, x, ucc, cc, ctx, y, scale, host, c_noise_dev, x_cl, t_in, T)
         ca = eng.cross_attn_vectors(ctx, T)          # conditioning is constant over the steps: computed once per sample
         for i in range(sig.numel() - 1):
             ops.sampler_prep(x, ucc, cc, BT, H, W, host[3][i], x_cl)
             t_in.copy_(c_noise_dev[i].expand(2 * BT))
             res = eng.forward_cl(x_cl, 2 * BT, H, W, t_in, ctx, y, T, ca=ca)
             ops.sampler_update(x, res, res.stride(0), BT, T, H, W, host[2][i], host[1][i], host[0][i], host[4][i], scale)
+        return x
+
+    def _run_fused_cfg_parallel(self, eng, x, ucc, cc, ctx, y, scale, host, c_noise_dev, x_cl, t_in, T):
+        """This rank's half of the CFG batch ([uc | c] on the batch axis) through the UNet, all_gather of the two halves."""
+        import torch.distributed as dist
+        BT, _, H, W = x.shape
+        r = dist.get_rank(self.cfg_group)
+        half = slice(r * BT, (r + 1) * BT)
+        ctx_h, y_h = ctx[half].contiguous(), y[half].contiguous()
+        ca = eng.cross_attn_vectors(ctx_h, T)
+        full = eng.pool.get("net_out_cfg", (2 * BT * H * W, 16), torch.float32)
+        parts = list(full.chunk(2, 0))
+        for i in range(len(host[0])):
+            ops.sampler_prep(x, ucc, cc, BT, H, W, host[3][i], x_cl)
+            t_in.copy_(c_noise_dev[i].expand(2 * BT))
+            res = eng.forward_cl(x_cl[half], BT, H, W, t_in[:BT], ctx_h, y_h, T, ca=ca)
+            dist.all_gather(parts, res, group=self.cfg_group)
+            ops.sampler_update(x, full, full.stride(0), BT, T, H, W, host[2][i], host[1][i], host[0][i], host[4][i], scale)
         return x

@@ -173,3 +173,119 @@ def test_clip_sharding_and_gather_world2_gloo():
     res = sorted(q.get(timeout=120) for _ in ps)
     [p.join(timeout=60) for p in ps]
     assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3] and all(r[2] for r in res)
+
+
+# ---- cfg-parallel (one clip over two ranks): host logic with a stand-in engine and torch versions of the two step kernels
+class _FakePool:
+    def __init__(self):
+        self.b = {}
+
+    def get(self, name, shape, dtype):
+        k = (name, tuple(shape), dtype)
+        if k not in self.b:
+            self.b[k] = torch.zeros(*shape, dtype=dtype)
+        return self.b[k]
+
+
+class _FakeEngine:
+    """forward_cl depends on every routed input (its batch slice of x_cl, ctx, y, t) so a mis-routed half is detected."""
+    AD = torch.float32
+
+    def __init__(self):
+        self.pool = _FakePool()
+
+    def cross_attn_vectors(self, ctx, T):
+        return ctx[:, 0, :4].clone()
+
+    def forward_cl(self, x_cl, n, H, W, t_in, ctx, y, T, ca=None):
+        res = torch.zeros(n * H * W, 16)
+        v = x_cl[..., :4] * 0.5 - x_cl[..., 4:8] * 0.25 + (ca[:, None, None, :] + y[:, None, None, :4]) * t_in.view(-1, 1, 1, 1) * 0.01
+        res[:, :4] = torch.tanh(v).reshape(n * H * W, 4)
+        return res
+
+
+class _FakeOps:
+    @staticmethod
+    def sampler_prep(x, ucc, cc, BT, H, W, c_in, x_cl):                      # elem.cu sampler_prep_kernel
+        xs = (x * c_in).permute(0, 2, 3, 1)
+        x_cl.zero_()
+        x_cl[:BT, ..., :4], x_cl[BT:, ..., :4] = xs, xs
+        x_cl[:BT, ..., 4:8], x_cl[BT:, ..., 4:8] = ucc.permute(0, 2, 3, 1), cc.permute(0, 2, 3, 1)
+
+    @staticmethod
+    def sampler_update(x, net, ld, BT, T, H, W, c_out, c_skip, sigma, dt, scale):   # elem.cu sampler_update_kernel
+        n4 = net.view(2 * BT, H, W, ld)[..., :4].permute(0, 3, 1, 2)
+        den = n4 * c_out + torch.cat([x, x]) * c_skip
+        du, dc = den[:BT], den[BT:]
+        d = du + scale.repeat(BT // T).view(BT, 1, 1, 1) * (dc - du)
+        x += dt * (x - d) / sigma
+
+
+def _cfg_case():
+    g = torch.Generator().manual_seed(11)
+    BT, T, H, W = 4, 2, 3, 5
+    r = lambda *s: torch.randn(*s, generator=g)
+    steps = 3
+    host = [[3.0, 2.0, 1.0], [0.3, 0.4, 0.5], [-0.9, -0.8, -0.7], [0.3, 0.45, 0.7], [-1.0, -1.0, -1.0]]
+    return dict(BT=BT, T=T, H=H, W=W, x=r(BT, 4, H, W), ucc=r(BT, 4, H, W), cc=r(BT, 4, H, W), ctx=r(2 * BT, 1, 8),
+                y=r(2 * BT, 6), scale=torch.tensor([1.0, 1.5]), host=host, c_noise=r(steps))
+
+
+def _cfg_run(group):
+    from gcd_b200 import sampling
+    k = _cfg_case()
+    eng = _FakeEngine()
+    smp = sampling.EulerEDMSampler.__new__(sampling.EulerEDMSampler)
+    smp.cfg_group = group
+    x = k["x"].clone()
+    x_cl = torch.zeros(2 * k["BT"], k["H"], k["W"], 64)
+    t_in = torch.zeros(2 * k["BT"])
+    old = sampling.ops
+    sampling.ops = _FakeOps
+    try:
+        if group is not None:
+            return smp._run_fused_cfg_parallel(eng, x, k["ucc"], k["cc"], k["ctx"], k["y"], k["scale"], k["host"], k["c_noise"],
+                                               x_cl, t_in, k["T"])
+        ca = eng.cross_attn_vectors(k["ctx"], k["T"])                      # the single-process loop of _run_fused
+        for i in range(3):
+            _FakeOps.sampler_prep(x, k["ucc"], k["cc"], k["BT"], k["H"], k["W"], k["host"][3][i], x_cl)
+            t_in.copy_(k["c_noise"][i].expand(2 * k["BT"]))
+            res = eng.forward_cl(x_cl, 2 * k["BT"], k["H"], k["W"], t_in, k["ctx"], k["y"], k["T"], ca=ca)
+            _FakeOps.sampler_update(x, res, 16, k["BT"], k["T"], k["H"], k["W"], k["host"][2][i], k["host"][1][i], k["host"][0][i],
+                                    k["host"][4][i], k["scale"])
+        return x
+    finally:
+        sampling.ops = old
+
+
+def _cfg_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    out = _cfg_run(dist.new_group([0, 1]))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_cfg_parallel_world2_gloo_equals_single_process():
+    """rank 0 = unconditional half, rank 1 = conditional half, one all_gather per step."""
+    import torch.multiprocessing as mp
+    ref = _cfg_run(None)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + os.getpid() % 500
+    ps = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = dict(q.get(timeout=120) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    assert torch.equal(res[0], res[1])
+    assert torch.allclose(res[0], ref, rtol=0, atol=1e-6)
+    from gcd_b200 import sampling
+    with pytest.raises(ValueError):
+        class G: pass
+        import torch.distributed as dist
+        orig = dist.get_world_size
+        dist.get_world_size = lambda g=None: 3
+        try:
+            sampling.EulerEDMSampler.set_cfg_parallel(sampling.EulerEDMSampler.__new__(sampling.EulerEDMSampler), G())
+        finally:
+            dist.get_world_size = orig

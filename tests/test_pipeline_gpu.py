@@ -173,3 +173,19 @@ def test_sampler_50_steps_scale_2p5_fused_equals_generic():
     b = sampler(sampling.FusedDenoiser(den, model, **extra), x.clone().cuda(), cond=cuda(c), uc=cuda(uc))
     assert sampler.last_path == "fused" and torch.isfinite(a).all()
     assert relerr(b, a) < 1e-2
+
+
+def test_cfg_parallel_two_gpus():
+    """SURVEY.md §8(f) rank 2 on real hardware (skipped on a 1-GPU box): one clip over two GPUs (uc | c) with NCCL equals the
+    single-GPU fused sampler within the 16-bit noise floor and leaves both ranks with bit-identical latents."""
+    import json
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(root, "tools", "cfg_parallel_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ranks_bit_identical"] and out["tiny_rel_l2_vs_single_gpu"] < 5e-3
