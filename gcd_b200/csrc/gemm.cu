@@ -98,6 +98,7 @@ struct TcParams {
     int w_batched;
     int stages;                 // smem ring depth (runtime: depends on which epilogue staging buffers are needed)
     int obufs;                  // output staging tiles per epilogue warpgroup (2 when the K loop is short)
+    int rbufs;                  // residual tiles in flight per epilogue warpgroup (2 when the K loop is short: HBM-latency bound)
     // epilogue
     const float* bias;
     const float* rowvec;
@@ -169,17 +170,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int OT = 16384;                                             // bytes of one output staging tile (128 x 128 B)
     const int RT1 = p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0, RT2 = p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0;
     uint8_t* sO = sB + STAGES * KC * B_BYTES;               // [2 warpgroups][obufs] output staging
-    uint8_t* sR1 = sO + 2 * p.obufs * OT;                   // [2] residual 1 (if any)
-    uint8_t* sR2 = sR1 + 2 * RT1;                           // [2] residual 2 (if any)
-    float* sBias = reinterpret_cast<float*>(sR2 + 2 * RT2); // [2][256] bias slice of the current tile, per warpgroup
+    uint8_t* sR1 = sO + 2 * p.obufs * OT;                   // [2 warpgroups][rbufs] residual 1 (if any)
+    uint8_t* sR2 = sR1 + 2 * p.rbufs * RT1;                 // [2 warpgroups][rbufs] residual 2 (if any)
+    float* sBias = reinterpret_cast<float*>(sR2 + 2 * p.rbufs * RT2); // [2][256] bias slice of the current tile, per warpgroup
     float* sStat = sBias + 512;             // [8 epilogue warps][32 groups][sum, sum of squares] (gn_acc only)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (p.gn_acc ? 512 : 0));
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + 8;            // [STAGES]  (STAGES <= 8)
     uint64_t* tfull = bars + 16;           // [2]
     uint64_t* tempty = bars + 18;          // [2]
-    uint64_t* rfull = bars + 20;           // [2] residual tiles landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t* rfull = bars + 20;           // [2 warpgroups][2] residual tiles landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -198,7 +199,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], PAIR ? 512 : 256);   // PAIR: the leader's MMA waits for both CTAs' epilogues
-            mbar_init(&rfull[i], 1);
+            mbar_init(&rfull[2 * i], 1); mbar_init(&rfull[2 * i + 1], 1);
         }
         fence_barrier_init();
     }
@@ -308,8 +309,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool has_res = p.has_r1 || p.has_r2;
         const uint32_t rbytes = (p.has_r1 ? (p.r1f32 ? 16384u : 8192u) : 0u) + (p.has_r2 ? (p.r2f32 ? 16384u : 8192u) : 0u);
         uint8_t* myObase = sO + g * p.obufs * OT;
-        uint8_t* myR1 = sR1 + g * RT1;
-        uint8_t* myR2 = sR2 + g * RT2;
+        uint8_t* myR1 = sR1 + g * p.rbufs * RT1;
+        uint8_t* myR2 = sR2 + g * p.rbufs * RT2;
+        uint32_t pfc = 0;                           // residual chunks prefetched by this warpgroup's leader
         float* myBias = sBias + g * 256;
         const int bar_id = 1 + g;
 
@@ -326,14 +328,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int nt = pf_tile % p.n_tiles, mt = (pf_tile / p.n_tiles) * CL + crank;
             const int tx = mt % p.ntx, ty = (mt / p.ntx) % p.nty, tz = mt / (p.ntx * p.nty);
             const int ncol = nt * BN + pf_s0 + pf_cc;
-            mbar_expect_tx(&rfull[g], rbytes);
-            if (p.has_r1) tma_load_4d(&mapR1, myR1, &rfull[g], ncol, tx * TW, ty * TH, tz * TN);
-            if (p.has_r2) tma_load_4d(&mapR2, myR2, &rfull[g], ncol, tx * TW, ty * TH, tz * TN);
+            const uint32_t pb = p.rbufs == 2 ? (pfc & 1) : 0;
+            pfc++;
+            mbar_expect_tx(&rfull[2 * g + pb], rbytes);
+            if (p.has_r1) tma_load_4d(&mapR1, myR1 + pb * RT1, &rfull[2 * g + pb], ncol, tx * TW, ty * TH, tz * TN);
+            if (p.has_r2) tma_load_4d(&mapR2, myR2 + pb * RT2, &rfull[2 * g + pb], ncol, tx * TW, ty * TH, tz * TN);
             const int width = min(pspan, min(BN - pf_s0, p.N - nt * BN - pf_s0));
             pf_cc += 32;
             if (pf_cc >= width) { pf_cc = 0; pf_s0 += 2 * pspan; }
         };
-        if (leader && has_res) prefetch_residual();
+        // with rbufs == 2 two residual chunks are always in flight per warpgroup: with one, each SM had at most 32 KB of loads
+        // outstanding (148 SMs x 32 KB / ~1.5 us HBM latency ~ 3.2 TB/s) — the measured ceiling of the fp32-residual linears
+        if (leader && has_res) { prefetch_residual(); if (p.rbufs == 2) prefetch_residual(); }
 
         uint32_t ci = 0, rc = 0;                    // spans / residual chunks processed by this warpgroup
         int it = 0;
@@ -447,10 +453,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         for (int j = 0; j < 32; j++) xf[j] *= p.a0;
                     }
                     if (has_res) {
-                        mbar_wait(&rfull[g], rc & 1);
+                        const uint32_t rb = p.rbufs == 2 ? (rc & 1) : 0;
+                        mbar_wait(&rfull[2 * g + rb], (p.rbufs == 2 ? (rc >> 1) : rc) & 1);
                         rc++;
-                        if (p.has_r1) add_residual_row(xf, myR1, r, p.r1f32, p.a1);
-                        if (p.has_r2) add_residual_row(xf, myR2, r, p.r2f32, p.a2);
+                        if (p.has_r1) add_residual_row(xf, myR1 + rb * RT1, r, p.r1f32, p.a1);
+                        if (p.has_r2) add_residual_row(xf, myR2 + rb * RT2, r, p.r2f32, p.a2);
                         if (cc + 32 < width) {                                 // more chunks in this span: recycle the buffer now
                             named_bar_sync(bar_id, 128);
                             if (leader) prefetch_residual();
@@ -569,8 +576,10 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     const int kiters = p.ntaps * p.kchunks;
     // short K loop => the epilogue is the critical path: double-buffer its staging tiles if >= 3 pipeline stages remain
     auto plan = [&](int fixed, int& obufs, int& stages) {
-        obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
-        stages = (TC_SMEM_MAX - (2 * obufs * OT + 2 * RT + fixed) - 256) / STAGE_BYTES;
+        // short K loop: first keep two residual chunks in flight (HBM latency), then double-buffer the output staging
+        p.rbufs = (RT > 0 && kiters <= 24 && (TC_SMEM_MAX - (2 * OT + 4 * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
+        obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * p.rbufs * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
+        stages = (TC_SMEM_MAX - (2 * obufs * OT + 2 * p.rbufs * RT + fixed) - 256) / STAGE_BYTES;
         if (stages > 8) stages = 8;
     };
     int fixed = 2048 /*bias*/, stages;
@@ -584,11 +593,11 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
         // ... unless the 2 KB of tables would leave fewer than 4 pipeline stages (then keep the direct global atomics)
         if (p.gn_groups == 32 && (int64_t)p.ntx * p.nty * p.ntz / n_img >= 4 * (int64_t)num_sms && ob2 == p.obufs && (st2 == stages || st2 >= 4)) {
             p.gn_acc = 1;
-            stages = st2;
             fixed += 2048;
         }
+        plan(fixed, p.obufs, stages);          // final plan (also restores rbufs when the tables were rejected)
     }
-    const int epi = 2 * p.obufs * OT + 2 * RT + fixed;
+    const int epi = 2 * p.obufs * OT + 2 * p.rbufs * RT + fixed;
     GCD_REQUIRE(stages >= 2, "tc_gemm: not enough shared memory for the pipeline (BN=%d)", BN);
     p.stages = stages;
     const int smem = stages * STAGE_BYTES + epi + 256;

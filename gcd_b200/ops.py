@@ -217,7 +217,10 @@ def groupnorm(x, n_img, rows, C, gamma, beta, eps, silu, out, stats, groups=32, 
     nbytes = n_img * groups * 2 * 8
     assert stats.dtype == torch.float64 and stats.numel() * 8 >= nbytes
     f32 = _is_f32(x)
-    with _timed("groupnorm", 0.0, n_img * rows * C * (((4 if f32 else 2) * (1 if have_stats else 2)) + 2)):
+    name = "groupnorm"
+    if _PROF is not None and DETAIL:
+        name = f"groupnorm n{n_img} rows{rows} C{C} f32={int(f32)} fused_stats={int(have_stats)}"
+    with _timed(name, 0.0, n_img * rows * C * (((4 if f32 else 2) * (1 if have_stats else 2)) + 2)):
         if not have_stats:
             check(L.gcd_memset_async(_p(stats), 0, nbytes, st), "memset")
             check(L.gcd_groupnorm_stats(_p(x), f32, n_img, rows, C, groups, _p(stats), st), "groupnorm_stats")
