@@ -176,8 +176,8 @@ attn_kernel(const __grid_constant__ CUtensorMap mapKV, const Params p) {
         if (SPLIT == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         // ---------------------------------------------------- softmax warps
-        // SPLIT threads share a query row (warps w and w+4 sit on the same TMEM lane quadrant): each owns NC key columns of
-        // the 64-key block and NC/... of the O columns; the row max (and at the end the row sum) is exchanged through smem.
+        // SPLIT threads share a query row (warps w and w+4 sit on the same TMEM lane quadrant): each owns NC of the block's 64
+        // key columns and the same NC of the 64 O columns; the row max (and at the end the row sum) is exchanged through smem.
         constexpr int NC = BK / SPLIT;
         const int q = warp & 3, half = (warp - 4) >> 2;
         const int r = q * 32 + lane;
