@@ -289,3 +289,25 @@ def test_cfg_parallel_world2_gloo_equals_single_process():
             sampling.EulerEDMSampler.set_cfg_parallel(sampling.EulerEDMSampler.__new__(sampling.EulerEDMSampler), G())
         finally:
             dist.get_world_size = orig
+
+
+# ------------------------------------------------------------------------------------------- bench.py contract (CPU legs)
+def test_bench_reference_arm_json_contract_and_no_cpu_fallback():
+    """`bench.py --impl reference` (the CPU port timed on the host cores) prints one JSON line with the contract's keys;
+    the product arm refuses to run without a CUDA device instead of falling back to the CPU."""
+    import json
+    import subprocess
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "latent-frames/sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
