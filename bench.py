@@ -184,6 +184,8 @@ def main():
     ust = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
     vst = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
     pipe.load_state(ust, vst)
+    if world > 1 or args.no_cpu_baseline:
+        ust = vst = None                      # 6 GB of host fp32 weights per rank: only the N=1 CPU-baseline leg reuses them
     # rank r samples its own clip: seed 1234 + r (scripts/test.py:1059-1084 strides examples over workers the same way)
     x0, c, uc, _ = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, LAT_H, LAT_W, seed=1234 + rank)
     pin = lambda t: t.pin_memory()
