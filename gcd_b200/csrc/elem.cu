@@ -102,6 +102,33 @@ extern "C" int gcd_timestep_embedding(const float* t, int n, int dim, float max_
     return 0;
 }
 
+// encoders/modules.py:247-287 (SphericalEmbedder): x[n,3] = (azimuth, elevation, radius) ->
+//   feat = [cos a, sin a, cos 2a, sin 2a, cos 4a, sin 4a, cos e, sin e, cos 2e, sin 2e, cos 4e, sin 4e, r],  out = feat W^T + b
+__global__ void spherical_embed_kernel(const float* __restrict__ x, int n, const float* __restrict__ w,
+                                       const float* __restrict__ b, int dim, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dim) return;
+    const int r = i / dim, o = i % dim;
+    const float a = x[r * 3], e = x[r * 3 + 1], rad = x[r * 3 + 2];
+    float f[13];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float m = (float)(1 << k);
+        f[2 * k] = cosf(a * m); f[2 * k + 1] = sinf(a * m);
+        f[6 + 2 * k] = cosf(e * m); f[7 + 2 * k] = sinf(e * m);
+    }
+    f[12] = rad;
+    float acc = 0.f;                       // same accumulation order as a 13-long dot product followed by the bias add
+#pragma unroll
+    for (int k = 0; k < 13; k++) acc = fmaf(f[k], w[o * 13 + k], acc);
+    out[i] = acc + b[o];
+}
+extern "C" int gcd_spherical_embed(const float* x, int n, const float* w, const float* b, int dim, float* out, void* stream) {
+    GCD_REQUIRE(x && w && b && out && n > 0 && dim > 0, "spherical_embed: bad arguments");
+    LAUNCH_1D(spherical_embed_kernel, (int64_t)n * dim, stream, x, n, w, b, dim, out);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ sampler
 // One thread per (image of the doubled batch, pixel): writes 64 act channels (128 B).
 __global__ void sampler_prep_kernel(const float* __restrict__ x, const float* __restrict__ ucc, const float* __restrict__ cc,

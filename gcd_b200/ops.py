@@ -313,6 +313,13 @@ def timestep_embedding(t, dim, out_act=None, out_f32=None, max_period=10000.0):
           "timestep_embedding")
 
 
+def spherical_embed(x, w, b, out):
+    """x: float32 [n, 3]; w: float32 [dim, 13]; b: float32 [dim] -> out float32 [n, dim] (SphericalEmbedder)."""
+    _need_cuda(x, w, b, out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 3 and w.is_contiguous() and w.shape[1] == 13
+    check(lib().gcd_spherical_embed(_p(x), x.shape[0], _p(w), _p(b), w.shape[0], _p(out), _stream()), "spherical_embed")
+
+
 def sampler_prep(x, uc_concat, c_concat, BT, H, W, c_in, out):
     _need_cuda(x, uc_concat, c_concat, out)
     check(lib().gcd_sampler_prep(_p(x), _p(uc_concat), _p(c_concat), BT, H, W, float(c_in), _p(out), _stream()),

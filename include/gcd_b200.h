@@ -137,6 +137,10 @@ int gcd_vae_time_mix(const float* in, int ld, int B, int T, int HW, const float*
 int gcd_timestep_embedding(const float* t, int n, int dim, float max_period, void* out_act, float* out_f32,
                            void* stream);
 
+/* SphericalEmbedder.forward (encoders/modules.py:247-287): x[n,3] = (azimuth, elevation, radius) float32
+ * -> out[n,dim] float32 = [cos/sin of 1x,2x,4x azimuth | same for elevation | radius] * w[dim,13]^T + b[dim]. */
+int gcd_spherical_embed(const float* x, int n, const float* w, const float* b, int dim, float* out, void* stream);
+
 /* ---- sampler step (sampling.py:101-121, denoiser.py:23-49, guiders.py:79-100, wrappers.py:23-34) ------------ */
 /* The scalar coefficients c_in/c_out/c_skip (denoiser_scaling.py:53-61) and dt = sigma_next - sigma_hat are computed
  * by the host with the same torch fp32 CPU ops as the reference and passed in, so scheduler arithmetic is bit-exact.

@@ -370,3 +370,21 @@ def encode_cond_frames(sd, cfg, x, quant_weight, quant_bias, scale_factor=0.1821
     (encoders/modules.py:1106)."""
     moments = F.conv2d(encoder_forward(sd, cfg, x), quant_weight, quant_bias)
     return moments[:, :cfg["z_channels"]] * scale_factor
+
+
+# ---------------------------------------------------------------------------------------------------------- small embedders
+def concat_timestep_embedder_nd(x, outdim):
+    """ConcatTimestepEmbedderND.forward (encoders/modules.py:1008-1016): each scalar of x[b, d] -> timestep_embedding(outdim),
+    "(b d) d2 -> b (d d2)"."""
+    if x.ndim == 1:
+        x = x[:, None]
+    b, dims = x.shape
+    return timestep_embedding(x.reshape(-1), outdim).reshape(b, dims * outdim)
+
+
+def spherical_embedder(proj_weight, proj_bias, x):
+    """SphericalEmbedder.forward (encoders/modules.py:255-287): cos/sin of 1x, 2x, 4x azimuth, the same for elevation, the raw
+    radius (13 features), then Linear(13, embed_dim)."""
+    az, el, rad = x[..., 0], x[..., 1], x[..., 2]
+    feats = [f(a * m) for a in (az, el) for m in (1.0, 2.0, 4.0) for f in (torch.cos, torch.sin)]
+    return F.linear(torch.stack(feats + [rad], dim=-1), proj_weight, proj_bias)

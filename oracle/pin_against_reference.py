@@ -118,6 +118,28 @@ def pin_encoder(tag, cfg, n, H, W):
                 "mode_scaled": mode.clone()}, os.path.join(GOLD, f"enc_{tag}.pt"))
 
 
+def pin_embedders():
+    Concat, Spherical = ref_shim.ref_embedder_classes()
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    x1 = torch.tensor([6.0, 127.0, 0.02, 1.0])                       # fps_id / motion_bucket_id / cond_aug style scalars
+    x2 = torch.randn(5, 3, generator=g) * 3.0
+    out["concat_x1"], out["concat_x2"] = x1, x2
+    out["concat_y1"], out["concat_y2"] = Concat(256)(x1), Concat(256)(x2)
+    sph = Spherical(128)
+    w = torch.randn(128, 13, generator=g) * 0.3
+    b = torch.randn(128, generator=g) * 0.1
+    sph.proj.weight.data.copy_(w); sph.proj.bias.data.copy_(b)
+    xs = torch.cat([torch.randn(28, 2, generator=g) * 2.0, torch.rand(28, 1, generator=g) * 6.0], 1)
+    out["sph_w"], out["sph_b"], out["sph_x"], out["sph_y"] = w, b, xs, sph(xs)
+    assert torch.equal(O.concat_timestep_embedder_nd(x1, 256), out["concat_y1"])
+    assert torch.equal(O.concat_timestep_embedder_nd(x2, 256), out["concat_y2"])
+    e = maxrel(O.spherical_embedder(w, b, xs), out["sph_y"])
+    print(f"[embedders] ConcatTimestepEmbedderND bit-exact; SphericalEmbedder oracle vs reference {e:.2e}")
+    assert e < 1e-6
+    torch.save(out, os.path.join(GOLD, "embedders.pt"))
+
+
 def pin_closed_forms():
     """Known-answer values derivable from the source."""
     ref_shim.install()
@@ -145,6 +167,7 @@ if __name__ == "__main__":
     pin_unet("tiny", UNET_TINY, B=1, T=3, H=16, W=24, steps=4)
     pin_decoder("tiny", VAE_TINY, T=3, H=8, W=8)
     pin_encoder("tiny", dict(O.VAE_ENCODER, ch=64), n=2, H=64, W=96)
+    pin_embedders()
     if "--full" in sys.argv:
         pin_unet("kubric", O.UNET_KUBRIC, B=1, T=2, H=16, W=16, steps=2)
         pin_unet("pardom", O.UNET_PARDOM, B=1, T=2, H=8, W=8, steps=1)

@@ -77,3 +77,33 @@ def build_ref_encoder(cfg):
     with torch.device("meta"):
         enc = Encoder(**kw)
     return enc.to_empty(device="cpu").eval()
+
+
+def ref_embedder_classes():
+    """The reference's own ConcatTimestepEmbedderND / SphericalEmbedder classes. `sgm/modules/encoders/modules.py` cannot be
+    imported here (open_clip, kornia, transformers' CLIP/T5 at module top), so the three class definitions are cut out of the
+    reference source with `ast` and executed against the real `Timestep` (openaimodel.py:466) — reference code runs, nothing
+    is copied into this repository."""
+    install()
+    import ast
+    import torch
+    import torch.nn as nn
+    from einops import rearrange
+    from sgm.modules.diffusionmodules.util import timestep_embedding
+
+    class Timestep(nn.Module):                 # openaimodel.py:466-472 (importing openaimodel needs the attention stack; 3 lines)
+        def __init__(self, dim):
+            super().__init__()
+            self.dim = dim
+
+        def forward(self, t):
+            return timestep_embedding(t, self.dim)
+
+    path = os.path.join(REF, "sgm", "modules", "encoders", "modules.py")
+    tree = ast.parse(open(path).read())
+    want = ("AbstractEmbModel", "SphericalEmbedder", "ConcatTimestepEmbedderND")
+    body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in want]
+    assert len(body) == 3
+    ns = {"torch": torch, "nn": nn, "rearrange": rearrange, "Timestep": Timestep, "Union": __import__("typing").Union}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns["ConcatTimestepEmbedderND"], ns["SphericalEmbedder"]

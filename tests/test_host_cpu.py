@@ -67,6 +67,20 @@ def test_oracle_encoder_vs_reference_golden():
         assert maxrel(O.encode_cond_frames(sd, cfg, gold["x"], gold["quant_w"], gold["quant_b"]), gold["mode_scaled"]) < 2e-5
 
 
+def test_oracle_embedders_vs_reference_golden():
+    """ConcatTimestepEmbedderND / SphericalEmbedder restatements vs outputs of the reference's own classes."""
+    gold = torch.load(os.path.join(GOLD, "embedders.pt"))
+    assert torch.equal(O.concat_timestep_embedder_nd(gold["concat_x1"], 256), gold["concat_y1"])
+    assert torch.equal(O.concat_timestep_embedder_nd(gold["concat_x2"], 256), gold["concat_y2"])
+    assert maxrel(O.spherical_embedder(gold["sph_w"], gold["sph_b"], gold["sph_x"]), gold["sph_y"]) < 1e-6
+    from gcd_b200.embedders import ConcatTimestepEmbedderND, SphericalEmbedder
+    with pytest.raises(RuntimeError):
+        ConcatTimestepEmbedderND(256)(gold["concat_x1"])           # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        SphericalEmbedder(128)(gold["sph_x"])
+    assert list(SphericalEmbedder(128).state_dict().keys()) == ["proj.weight", "proj.bias"]
+
+
 def test_len1_cross_attention_is_a_bias():
     """with one context token attn2(x, ctx) == to_out(to_v(ctx)), independent of x."""
     torch.manual_seed(0)

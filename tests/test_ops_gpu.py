@@ -1,5 +1,6 @@
 """GPU parity tests of the individual C-ABI ops against plain torch fp32 math on the same (16-bit rounded) inputs."""
 import math
+import os
 
 import pytest
 import torch
@@ -298,3 +299,22 @@ def test_fused_groupnorm_stats(ops, out_f32):
     x2 = rnd(4, 4, 6, 64, dtype=AD)
     out2 = torch.empty(4 * 4 * 6, Co, device="cuda")
     assert not ops.conv2d_3x3(x2, wp, ops.make_ep(out2, bias=bias, gn_stats=(st, Co // 32, 32, 24)))
+
+
+def test_conditioner_embedders_vs_reference(ops):
+    """ConcatTimestepEmbedderND and SphericalEmbedder (one kernel each) vs the reference classes' outputs."""
+    from gcd_b200.embedders import ConcatTimestepEmbedderND, SphericalEmbedder
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "embedders.pt"))
+    emb = ConcatTimestepEmbedderND(256)
+    for k in ("1", "2"):
+        y = emb(gold["concat_x" + k].cuda())
+        assert y.shape == gold["concat_y" + k].shape and y.dtype == torch.float32
+        # arguments reach 127 * 1 = 127 rad: cosf/sinf of the device vs the host libm agree to a few ulp of the argument
+        assert (y.cpu() - gold["concat_y" + k]).abs().max() < 2e-5
+    sph = SphericalEmbedder(128)
+    sph.load_state_dict({"proj.weight": gold["sph_w"], "proj.bias": gold["sph_b"]})
+    sph = sph.cuda()
+    y = sph(gold["sph_x"].cuda())
+    assert y.shape == gold["sph_y"].shape
+    assert (y.cpu() - gold["sph_y"]).abs().max() < 1e-5 * max(1.0, float(gold["sph_y"].abs().max()))
+    assert sph(gold["sph_x"].cuda().view(2, 14, 3)).shape == (2, 14, 128)
