@@ -34,6 +34,8 @@ WORKLOADS = {
     "kubric": dict(unet="UNET_KUBRIC", steps=25, max_scale=1.5, name="Kubric-4D gradual max90, 25-step Euler sample, 14x72x128 latent (576x1024 px)"),
     "pardom": dict(unet="UNET_PARDOM", steps=25, max_scale=1.5, name="ParallelDomain-4D gradual RGB, 25-step sample, 14x72x128 latent"),
     "direct50": dict(unet="UNET_KUBRIC", steps=50, max_scale=2.5, name="Kubric-4D direct max180, CFG 2.5, 50-step sample, 14x72x128 latent"),
+    # reduced-width network: only for tests of this script's plumbing (tests/test_host_cpu.py), never a reported number
+    "tiny-selftest": dict(unet="UNET_TINY", vae="VAE_TINY", steps=25, max_scale=1.5, name="SELF-TEST ONLY: width-64 network, not a benchmark"),
 }
 
 
@@ -126,7 +128,7 @@ def run_reference(args, wl):
         return
     from gcd_b200 import spec
     from gcd_b200 import synthetic
-    unet_cfg, vae_cfg = getattr(spec, wl["unet"]), spec.VAE_DECODER
+    unet_cfg, vae_cfg = getattr(spec, wl["unet"]), getattr(spec, wl.get("vae", "VAE_DECODER"))
     ust = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
     vst = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
     vals = []
@@ -179,7 +181,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=1200))   # ranks build 1.5 B seeded weights on shared host cores first
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
-    unet_cfg, vae_cfg = getattr(spec, wl["unet"]), spec.VAE_DECODER
+    unet_cfg, vae_cfg = getattr(spec, wl["unet"]), getattr(spec, wl.get("vae", "VAE_DECODER"))
     pipe = GCDHotPath(unet_cfg, vae_cfg, num_steps=wl["steps"], num_frames=T_FRAMES, max_scale=wl["max_scale"], device=dev)
     ust = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
     vst = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
