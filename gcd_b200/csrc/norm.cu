@@ -55,6 +55,47 @@ __global__ void gn_stats_kernel(const void* __restrict__ in, int64_t rows, int C
     }
 }
 
+// Channel concat of two fp32 tensors fused with the GroupNorm statistics of the result (the UNet's skip concatenations,
+// openaimodel.py `th.cat([h, hs.pop()], dim=1)` followed by the ResBlock's first GroupNorm): same geometry and the same
+// deterministic reduction as gn_stats_kernel; saves the statistics pass over the concatenated tensor.
+__global__ void concat_stats_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b, int Cb, int64_t rows,
+                                    int cpg, int rows_per_block, float* __restrict__ out, double* __restrict__ stats,
+                                    int groups) {
+    extern __shared__ float sm[];                      // [blockDim.y][C/2][2]
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    const int C = Ca + Cb;
+    const int c = threadIdx.x * 4;
+    const bool from_a = c < Ca;                        // Ca is a multiple of 4: a thread's 4 channels come from one source
+    const float* src = from_a ? a + c : b + (c - Ca);
+    const int ld = from_a ? Ca : Cb;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const int64_t row = (int64_t)img * rows + r;
+        const float4 v = *reinterpret_cast<const float4*>(src + row * ld);
+        *reinterpret_cast<float4*>(out + row * C + c) = v;
+        sa += v.x + v.y; qa += v.x * v.x + v.y * v.y;
+        sb += v.z + v.w; qb += v.z * v.z + v.w * v.w;
+    }
+    const int npairs = C >> 1;
+    float* mine = sm + ((size_t)threadIdx.y * npairs + 2 * threadIdx.x) * 2;
+    mine[0] = sa; mine[1] = qa; mine[2] = sb; mine[3] = qb;
+    __syncthreads();
+    if (tid < groups) {
+        const int ppg = cpg >> 1;
+        double s = 0.0, q = 0.0;
+        for (int y = 0; y < (int)blockDim.y; y++) {
+            const float* row = sm + ((size_t)y * npairs + (size_t)tid * ppg) * 2;
+            for (int pp = 0; pp < ppg; pp++) { s += (double)row[2 * pp]; q += (double)row[2 * pp + 1]; }
+        }
+        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 0], s);
+        atomicAdd(&stats[((int64_t)img * groups + tid) * 2 + 1], q);
+    }
+}
+
 template <bool IN_F32>
 __global__ void gn_apply_kernel(const void* __restrict__ in, int64_t rows, int C, int cpg, int rows_per_block,
                                 const double* __restrict__ stats, int groups, const float* __restrict__ gamma,
@@ -132,6 +173,22 @@ extern "C" int gcd_groupnorm_stats(const void* in, int in_f32, int64_t n_img, in
         gn_stats_kernel<true><<<grid, block, smem, st>>>(in, rows, C, C / groups, rpb, stats, groups);
     else
         gn_stats_kernel<false><<<grid, block, smem, st>>>(in, rows, C, C / groups, rpb, stats, groups);
+    GCD_CUDA_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+extern "C" int gcd_concat_channels_stats(const float* a, int Ca, const float* b, int Cb, int64_t n_img, int64_t rows,
+                                         int groups, float* out, double* stats, void* stream) {
+    GCD_REQUIRE(a && b && out && stats && Ca % 4 == 0 && Cb % 4 == 0, "concat_stats: channel counts must be multiples of 4");
+    dim3 grid, block;
+    int rpb;
+    const int C = Ca + Cb;
+    int rc = gn_geometry(n_img, rows, C, groups, &grid, &block, &rpb);
+    if (rc) return rc;
+    const size_t smem = (size_t)block.y * (C / 2) * 2 * sizeof(float);
+    GCD_REQUIRE(smem <= 48 * 1024 && (int)(block.x * block.y) >= groups, "concat_stats: unsupported geometry (C=%d)", C);
+    concat_stats_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(a, Ca, b, Cb, rows, C / groups, rpb, out, stats, groups);
     GCD_CUDA_CHECK(cudaGetLastError());
     g_launches++;
     return 0;

@@ -271,11 +271,20 @@ def upsample2x_to_act(x, n, H, W, C, out):
     check(lib().gcd_upsample2x_to_act(_p(x), n, H, W, C, _p(out), _stream()), "upsample2x")
 
 
-def concat_channels(a, b, out):
-    _need_cuda(a, b, out)
+def concat_channels(a, b, out, stats=None, n_img=None, groups=32):
+    """out[rows, Ca+Cb] = cat(a, b) along channels (float32). With `stats` (zeroed float64 [n_img*groups*2]) the GroupNorm
+    statistics of `out` per (image, group) are accumulated in the same pass."""
+    _need_cuda(a, b, out, stats)
     rows = a.shape[0]
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
-    check(lib().gcd_concat_channels(_p(a), a.shape[1], _p(b), b.shape[1], rows, _p(out), _stream()), "concat")
+    if stats is None:
+        check(lib().gcd_concat_channels(_p(a), a.shape[1], _p(b), b.shape[1], rows, _p(out), _stream()), "concat")
+        return
+    assert stats.dtype == torch.float64 and rows % n_img == 0 and stats.numel() >= n_img * groups * 2
+    C = a.shape[1] + b.shape[1]
+    with _timed("groupnorm", 0.0, rows * C * 8):
+        check(lib().gcd_concat_channels_stats(_p(a), a.shape[1], _p(b), b.shape[1], n_img, rows // n_img, groups, _p(out),
+                                              _p(stats), _stream()), "concat_stats")
 
 
 def silu_act(x, out):

@@ -40,6 +40,9 @@ def register_param_tree(root, shapes, init=None):
         mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
 
 
+FUSE_CONCAT_STATS = True      # skip-concat kernel also produces the following GroupNorm's statistics
+
+
 class BufferPool:
     """Named device workspaces, allocated once per (name, shape, dtype) and reused across blocks and steps."""
 
@@ -404,9 +407,15 @@ class UNetEngine:
             if (sH, sW) != (hH, hW):
                 raise ValueError(f"skip/upsample size mismatch {(sH, sW)} vs {(hH, hW)}: latent H, W must be divisible by 8")
             cat = pool.get(f"cat{bi}", (n * hH * hW, hC + sC), torch.float32)
-            ops.concat_channels(h, s, cat)
-            # the concatenated tensor regroups channels: its GroupNorm statistics cannot reuse the producers' sums
-            h, hH, hW, hC, hst = run(layers, cat, hH, hW, hC + sC, bi, "out", None)
+            # the concatenated tensor regroups channels: its GroupNorm statistics cannot reuse the producers' sums, but the
+            # concat pass itself can accumulate them (saves the separate statistics read of the largest fp32 tensors)
+            cst = None
+            if FUSE_CONCAT_STATS:
+                cst, _ = self._stats_req(n, hC + sC, hH * hW)
+                ops.concat_channels(h, s, cat, stats=cst, n_img=n)
+            else:
+                ops.concat_channels(h, s, cat)
+            h, hH, hW, hC, hst = run(layers, cat, hH, hW, hC + sC, bi, "out", cst)
         rows = n * hH * hW
         a = pool.get(f"act_a{hC}", (rows, hC), AD)
         self._gn(h, n, hH * hW, hC, "out.0", 1e-5, True, a, stats=hst)

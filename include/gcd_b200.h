@@ -120,6 +120,11 @@ int gcd_cast_f32_to_act(const float* in, int64_t n, void* out, void* stream);
 int gcd_upsample2x_to_act(const float* in, int n, int H, int W, int C, void* out, void* stream);
 /* channel concat of two float32 channels-last tensors: out[r, :Ca]=a, out[r, Ca:]=b  (video_model.py:525 th.cat) */
 int gcd_concat_channels(const float* a, int Ca, const float* b, int Cb, int64_t rows, float* out, void* stream);
+/* the same concat of [n_img*rows, Ca] and [n_img*rows, Cb] fused with the GroupNorm statistics of the result (the skip concat
+ * of the UNet's output blocks feeds a ResBlock whose first op is GroupNorm32, openaimodel.py / video_model.py:536-540):
+ * stats[n_img, groups, 2] float64 (sum, sum of squares), zeroed by the caller, accumulated in a fixed order per block. */
+int gcd_concat_channels_stats(const float* a, int Ca, const float* b, int Cb, int64_t n_img, int64_t rows, int groups,
+                              float* out, double* stats, void* stream);
 /* act(x) on act tensor: SiLU (emb_layers SiLU, openaimodel.py:262-268) */
 int gcd_silu_act(const void* in, int64_t n, void* out, void* stream);
 /* SiLU on a float32 tensor, written as act (emb_layers' nn.SiLU on `emb`, openaimodel.py:262-268) */

@@ -318,3 +318,31 @@ def test_conditioner_embedders_vs_reference(ops):
     assert y.shape == gold["sph_y"].shape
     assert (y.cpu() - gold["sph_y"]).abs().max() < 1e-5 * max(1.0, float(gold["sph_y"].abs().max()))
     assert sph(gold["sph_x"].cuda().view(2, 14, 3)).shape == (2, 14, 128)
+
+
+@pytest.mark.parametrize("n,rows,Ca,Cb", [(28, 9216, 640, 320), (28, 9216, 320, 320), (28, 144, 1280, 1280), (3, 100, 64, 192)])
+def test_concat_channels_with_fused_groupnorm_stats(ops, n, rows, Ca, Cb):
+    """Skip concat of the UNet's output blocks: one pass writes cat(a, b) and the (image, group) sums for the next GroupNorm."""
+    a, b = rnd(n * rows, Ca) + 0.3, rnd(n * rows, Cb) * 2.0
+    out = torch.empty(n * rows, Ca + Cb, device="cuda")
+    st = torch.zeros(max(n, 64) * 64, device="cuda", dtype=torch.float64)
+    ops.concat_channels(a, b, out, stats=st, n_img=n)
+    ref = torch.cat([a, b], 1)
+    assert torch.equal(out, ref)
+    v = ref.double().view(n, rows, 32, (Ca + Cb) // 32)
+    want = torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1).reshape(-1)
+    assert torch.allclose(st[: n * 64], want, rtol=2e-6, atol=1e-3)
+    st2 = torch.zeros_like(st)
+    ops.concat_channels(a, b, out, stats=st2, n_img=n)
+    assert torch.equal(st, st2)                       # fixed summation order inside a block; fp64 atomics across blocks
+    # consumer equivalence: GroupNorm with these statistics == GroupNorm with its own statistics pass
+    g, be = rnd(Ca + Cb) * 0.1 + 1, rnd(Ca + Cb) * 0.1
+    AD = ops.act_dtype()
+    y1 = torch.empty(n * rows, Ca + Cb, device="cuda", dtype=AD)
+    y2 = torch.empty_like(y1)
+    ops.groupnorm(out, n, rows, Ca + Cb, g, be, 1e-5, True, y1, st, have_stats=True)
+    ops.groupnorm(out, n, rows, Ca + Cb, g, be, 1e-5, True, y2, torch.empty_like(st))
+    assert relerr(y1, y2) < 1e-5
+    out2 = torch.empty_like(out)
+    ops.concat_channels(a, b, out2)                   # plain variant unchanged
+    assert torch.equal(out2, ref)
