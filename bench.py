@@ -265,13 +265,14 @@ def main():
         tc_tflops = tc["flops"] / (tc["ms"] / 1e3) / 1e12
         per_frame = flops.clip_flops(unet_cfg, vae_cfg, T_FRAMES, LAT_H, LAT_W, wl["steps"]) / T_FRAMES
         path_tflops = per_frame * (value / world) / 1e12
-        traffic = None
+        traffic, traffic_detail = None, None
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp))       # dram bytes of one representative tc_gemm launch from `ncu --set full`
+            traffic_detail = json.load(open(tp))       # one representative tc_gemm launch from `ncu --set full`
+            traffic = traffic_detail.get("dram_bytes")  # dram__bytes_read.sum + dram__bytes_write.sum of that launch
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv / linear)",
                 "achieved": round(tc_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(tc_tflops / pk["tflops"], 4),
-                "traffic": traffic, "peak_source": pk["src"],
+                "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": pk["src"],
                 "kernel_share_of_step": round(tc["ms"] / max(tot_ms, 1e-9), 4),
                 "whole_path": {"algorithmic_tflop_per_latent_frame": round(per_frame / 1e12, 1),
                                "achieved": round(path_tflops, 1), "frac": round(path_tflops / pk["tflops"], 4)},
