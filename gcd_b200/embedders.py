@@ -13,10 +13,25 @@ import torch.nn as nn
 from . import ops
 
 
-class _EmbBase(nn.Module):
+def _reference_base():
+    """The reference GeneralConditioner asserts `isinstance(embedder, AbstractEmbModel)` (encoders/modules.py:93-96): when
+    `sgm` imports, derive from its AbstractEmbModel so a YAML `target:` swap passes that gate; standalone, a plain nn.Module
+    carrying the same three attributes (encoders/modules.py:40-81)."""
+    try:
+        from sgm.modules.encoders.modules import AbstractEmbModel as Ref   # noqa: WPS433
+        return Ref
+    except Exception:
+        return nn.Module
+
+
+_RefBase = _reference_base()
+
+
+class _EmbBase(_RefBase):
     def __init__(self):
         super().__init__()
-        self.is_trainable, self.ucg_rate, self.input_key = None, None, None
+        if _RefBase is nn.Module:
+            self.is_trainable, self.ucg_rate, self.input_key = None, None, None
 
     @staticmethod
     def _need_cuda(x, who):

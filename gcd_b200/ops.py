@@ -337,9 +337,20 @@ def sampler_prep(x, uc_concat, c_concat, BT, H, W, c_in, out):
 
 def sampler_update(x, net_out, ld_net, BT, T, H, W, c_out, c_skip, sigma, dt, scale):
     _need_cuda(x, net_out, scale)
+    assert scale.dtype == torch.float32 and scale.numel() == T, "guidance scale must hold one float32 per frame of a clip"
     check(lib().gcd_sampler_update(_p(x), _p(net_out), ld_net, BT, T, H, W, float(c_out), float(c_skip), float(sigma),
                                    float(dt), _p(scale), _stream()), "sampler_update")
 
 
+_REPLAYED = 0
+
+
+def count_replayed_launches(n):
+    """Kernel launches executed by replaying a captured CUDA graph (the library's own counter only sees the capture)."""
+    global _REPLAYED
+    _REPLAYED += int(n)
+
+
 def launch_count():
-    return int(lib().gcd_launch_count())
+    """Kernels of libgcd_b200.so launched so far: direct launches + nodes of replayed CUDA graphs."""
+    return int(lib().gcd_launch_count()) + _REPLAYED

@@ -18,6 +18,7 @@ Two execution paths, identical arithmetic:
 The scalar schedule (sigmas, c_*, dt) is always computed with the same torch fp32 ops as the reference.
 """
 import importlib
+import warnings
 
 import torch
 import torch.nn as nn
@@ -176,6 +177,7 @@ def _unwrap_closure(fn):
 
 class EulerEDMSampler:
     """sampling.py:26-144,225-230 (BaseDiffusionSampler + EDMSampler + EulerEDMSampler)."""
+    _warned_generic = False
 
     def __init__(self, discretization_config, num_steps=None, guider_config=None, verbose=False, device="cuda",
                  s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
@@ -187,6 +189,7 @@ class EulerEDMSampler:
         self.verbose, self.device = verbose, device
         self.s_churn, self.s_tmin, self.s_tmax, self.s_noise = s_churn, s_tmin, s_tmax, s_noise
         self.last_path = None
+        self.trace_steps, self.trace = (), {}   # tests: keep a copy of x after these step counts (fused path), e.g. {1, 5, 10}
         self.cfg_group = None            # set_cfg_parallel(): 2-rank process group splitting the CFG pair of ONE clip
 
     def set_cfg_parallel(self, group):
@@ -202,7 +205,10 @@ class EulerEDMSampler:
 
     # ---- reference control flow -------------------------------------------------------------------------------
     def prepare_sampling_loop(self, x, cond, uc=None, num_steps=None):
-        sigmas = self.discretization(self.num_steps if num_steps is None else num_steps, device=self.device)
+        # The schedule is evaluated on the HOST with the reference's fp32 expressions and shipped to the device: torch's CUDA
+        # `pow`/`linspace` need not round like the CPU ones, and the reference goldens (tests/golden/closed_forms.pt) are CPU
+        # values — this keeps the scheduler bit-exact whatever `self.device` is (tests/test_pipeline_gpu.py asserts it).
+        sigmas = self.discretization(self.num_steps if num_steps is None else num_steps, device="cpu").to(self.device)
         uc = cond if uc is None else uc
         x *= torch.sqrt(1.0 + sigmas[0] ** 2.0)
         return x, x.new_ones([x.shape[0]]), sigmas, len(sigmas), cond, uc
@@ -231,6 +237,12 @@ class EulerEDMSampler:
             self.last_path = "fused"
             return self._run_fused(fused, x, sigmas, cond, uc)
         self.last_path = "generic"
+        if not EulerEDMSampler._warned_generic and x.is_cuda:
+            EulerEDMSampler._warned_generic = True
+            warnings.warn("gcd_b200.EulerEDMSampler: denoiser closure / guider / conditioning not recognised as the GCD "
+                          "sample_video configuration -> generic path (reference control flow with torch glue per step; the "
+                          "UNet still runs the CUDA kernels). Pass a gcd_b200.sampling.FusedDenoiser for the fused path.",
+                          RuntimeWarning, stacklevel=2)
         for i in range(num_sigmas - 1):
             x = self.sampler_step(s_in * sigmas[i], s_in * sigmas[i + 1], denoiser, x, cond, uc,
                                   self._gamma(sigmas, i, num_sigmas))
@@ -255,6 +267,8 @@ class EulerEDMSampler:
         ioi = extra.get("image_only_indicator")
         if T != self.guider.num_frames or x.shape[0] % T != 0 or (ioi is not None and bool((ioi != 0).any())):
             return None
+        if self.guider.scale.numel() != T:      # num_frames mutated after construction (scripts/eval_utils.py:170): `scale` is
+            return None                         # stale — the generic path then fails with the reference's own shape error
         if cond["concat"].shape != x.shape or uc_["concat"].shape != x.shape:
             return None
         return dict(net=net, scaling=den.scaling, T=T)
@@ -268,8 +282,13 @@ class EulerEDMSampler:
         x = x.contiguous()
         cc = cond["concat"].to(torch.float32).contiguous()
         ucc = uc["concat"].to(torch.float32).contiguous()
-        ctx = torch.cat((uc["crossattn"], cond["crossattn"]), 0).contiguous()      # guiders.py:89-100
-        y = torch.cat((uc["vector"], cond["vector"]), 0).contiguous()
+        # conditioning goes into pool buffers: fixed addresses let the captured CUDA graph of the forward serve every sample
+        ctx_new = torch.cat((uc["crossattn"], cond["crossattn"]), 0)               # guiders.py:89-100
+        y_new = torch.cat((uc["vector"], cond["vector"]), 0)
+        ctx = eng.pool.get("ctx_static", tuple(ctx_new.shape), ctx_new.dtype)
+        y = eng.pool.get("y_static", tuple(y_new.shape), y_new.dtype)
+        ctx.copy_(ctx_new)
+        y.copy_(y_new)
         scale = self.guider.scale.reshape(-1).to(dev, torch.float32).contiguous()
         # scalar schedule with the reference's own tensor ops (on the sigmas' device), read back once
         sig = sigmas.to(torch.float32)
@@ -281,12 +300,14 @@ class EulerEDMSampler:
         t_in = eng.pool.get("t_in", (2 * BT,), torch.float32)
         if self.cfg_group is not None:
             return self._run_fused_cfg_parallel(eng, x, ucc, cc, ctx, y, scale, host, c_noise_dev, x_cl, t_in, T)
-        ca = eng.cross_attn_vectors(ctx, T)          # conditioning is constant over the steps: computed once per sample
+        ca = eng.cross_attn_vectors(ctx, T, static=True)   # constant over the steps: computed once per sample
         for i in range(sig.numel() - 1):
             ops.sampler_prep(x, ucc, cc, BT, H, W, host[3][i], x_cl)
             t_in.copy_(c_noise_dev[i].expand(2 * BT))
-            res = eng.forward_cl(x_cl, 2 * BT, H, W, t_in, ctx, y, T, ca=ca)
+            res = eng.forward_graphed(x_cl, 2 * BT, H, W, t_in, ctx, y, T, ca)
             ops.sampler_update(x, res, res.stride(0), BT, T, H, W, host[2][i], host[1][i], host[0][i], host[4][i], scale)
+            if (i + 1) in self.trace_steps:
+                self.trace[i + 1] = x.clone()
         return x
 
     def _run_fused_cfg_parallel(self, eng, x, ucc, cc, ctx, y, scale, host, c_noise_dev, x_cl, t_in, T):
@@ -295,14 +316,14 @@ class EulerEDMSampler:
         BT, _, H, W = x.shape
         r = dist.get_rank(self.cfg_group)
         half = slice(r * BT, (r + 1) * BT)
-        ctx_h, y_h = ctx[half].contiguous(), y[half].contiguous()
-        ca = eng.cross_attn_vectors(ctx_h, T)
+        ctx_h, y_h = ctx[half], y[half]              # contiguous views of the static pool buffers
+        ca = eng.cross_attn_vectors(ctx_h, T, static=True)
         full = eng.pool.get("net_out_cfg", (2 * BT * H * W, 16), torch.float32)
         parts = list(full.chunk(2, 0))
         for i in range(len(host[0])):
             ops.sampler_prep(x, ucc, cc, BT, H, W, host[3][i], x_cl)
             t_in.copy_(c_noise_dev[i].expand(2 * BT))
-            res = eng.forward_cl(x_cl[half], BT, H, W, t_in[:BT], ctx_h, y_h, T, ca=ca)
+            res = eng.forward_graphed(x_cl[half], BT, H, W, t_in[:BT], ctx_h, y_h, T, ca)
             dist.all_gather(parts, res, group=self.cfg_group)
             ops.sampler_update(x, full, full.stride(0), BT, T, H, W, host[2][i], host[1][i], host[0][i], host[4][i], scale)
         return x

@@ -15,6 +15,7 @@ Exact algebraic shortcuts taken (all parity-tested a
   - image_only_indicator is all zeros => AlphaBlender alpha = sigmoid(mix_factor) (scalar per blender).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -37,7 +38,21 @@ def register_param_tree(root, shapes, init=None):
                 mod.add_module(p, _Node())
             mod = getattr(mod, p)
         t = torch.zeros(shape) if init is None else init(key, shape)
-        mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+        # requires_grad=True like any nn.Module parameter: the reference's LitEma (modules/ema.py) only shadows parameters
+        # with requires_grad, and DiffusionEngine.ema_scope swaps them in with `param.data.copy_` — see weights_key()
+        mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=True))
+
+
+def weights_key(module, device):
+    """Cache key of a drop-in module's packed engine: (data_ptr, _version) of every parameter PLUS a content probe of nine
+    tensors spread over the parameter list. `_version` alone misses `param.data.copy_(...)` — exactly what the reference's
+    LitEma.copy_to / restore do (modules/ema.py) — so an EMA swap would otherwise keep running the stale packed weights.
+    Costs one small device->host read per engine() call (once per sample on the fused path)."""
+    ps = list(module.parameters())
+    meta = tuple((p.data_ptr(), p._version) for p in ps)
+    probe = ps[::max(1, len(ps) // 8)][:8] + [ps[-1]]
+    vals = torch.stack([p.detach().reshape(-1)[:512].double().sum().cpu() for p in probe]).tolist()
+    return (str(device), meta, tuple(vals))
 
 
 FUSE_CONCAT_STATS = True      # skip-concat kernel also produces the following GroupNorm's statistics
@@ -81,6 +96,8 @@ class UNetEngine:
         self.w = {}
         self._pe_cache = {}
         self.debug = None          # set to a list to record every layer's output (tools/bisect_batch.py)
+        self.use_graphs = os.environ.get("GCD_NO_GRAPH", "0") != "1"
+        self._graphs = {}
         self._pack(state)
 
     # ------------------------------------------------------------------------------------------------ weight packing
@@ -213,11 +230,12 @@ class UNetEngine:
             self._pe_cache[key] = pe
         return self._pe_cache[key]
 
-    def cross_attn_vectors(self, context, T):
+    def cross_attn_vectors(self, context, T, static=False):
         """len-1 cross attention == to_out(to_v(ctx)) (+bias): per frame for the spatial blocks, per clip
         (context[::T], video_attention.py:249-253) for the temporal blocks. Step-invariant: the fused sampler computes
         it once per sample and passes it to every step; a plain forward() recomputes it (no pointer-keyed caching —
-        a recycled allocation with new contents must never hit a stale entry)."""
+        a recycled allocation with new contents must never hit a stale entry). `static`: write into pool buffers (fixed
+        addresses across samples, so a captured CUDA graph of the forward can be replayed for the next sample)."""
         if context.dim() != 3 or context.shape[1] != 1:
             raise NotImplementedError(
                 f"gcd_b200.VideoUNet supports the GCD conditioning layout context=[BT,1,D] only, got {tuple(context.shape)}")
@@ -230,9 +248,13 @@ class UNetEngine:
                 if kind != "svt":
                     continue
                 for blk, c in ((p + ".transformer_blocks.0", ctx), (p + ".time_stack.0", ctx_t)):
-                    v = torch.empty(c.shape[0], cout, device=self.device, dtype=self.AD)
+                    if static:
+                        v = self.pool.get("ca_v", (c.shape[0], cout), self.AD)
+                        o = self.pool.get("ca:" + blk, (c.shape[0], cout), torch.float32)
+                    else:
+                        v = torch.empty(c.shape[0], cout, device=self.device, dtype=self.AD)
+                        o = torch.empty(c.shape[0], cout, device=self.device, dtype=torch.float32)
                     ops.linear(c, self.w[blk + ".attn2.v.w"], ops.make_ep(v))
-                    o = torch.empty(c.shape[0], cout, device=self.device, dtype=torch.float32)
                     ops.linear(v, self.w[blk + ".attn2.out.w"], ops.make_ep(o, bias=self.w[blk + ".attn2.out.b"]))
                     vecs[blk] = o
         return vecs
@@ -348,6 +370,32 @@ class UNetEngine:
         emb_all = pool.get("emb_all", (n, self.emb_total), torch.float32)
         ops.linear(es, W["emb_all.w"], ops.make_ep(emb_all, bias=W["emb_all.b"]))
         return emb_all
+
+    def forward_graphed(self, x_cl, n, H, Wd, timesteps, context, y, T, ca):
+        """forward_cl replayed from a CUDA graph: ~620 kernel launches per CFG forward, each with six host
+        `cuTensorMapEncodeTiled` calls and ctypes marshalling, become one `cudaGraphLaunch`. The tensor maps are
+        __grid_constant__ kernel parameters, i.e. baked into the graph's kernel nodes, so every input must keep its ADDRESS
+        between replays: the fused sampler passes pool buffers (x_cl, t_in, ctx / y copies, static cross-attention vectors).
+        Keyed on shapes + those addresses; the first call for a key runs eagerly once (allocates workspaces, configures the
+        kernels), captures, then replays. Disabled under ops.profile (per-launch events) and with GCD_NO_GRAPH=1."""
+        if not self.use_graphs or ops._PROF is not None or self.debug is not None:
+            return self.forward_cl(x_cl, n, H, Wd, timesteps, context, y, T, ca=ca)
+        key = (n, H, Wd, T, x_cl.data_ptr(), timesteps.data_ptr(), context.data_ptr(), y.data_ptr(),
+               tuple(v.data_ptr() for v in ca.values()))
+        ent = self._graphs.get(key)
+        if ent is None:
+            self.forward_cl(x_cl, n, H, Wd, timesteps, context, y, T, ca=ca)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                res = self.forward_cl(x_cl, n, H, Wd, timesteps, context, y, T, ca=ca)
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._graphs[key] = (graph, res, ops.launch_count() - l0)
+        ent[0].replay()
+        ops.count_replayed_launches(ent[2])
+        return ent[1]
 
     def forward_cl(self, x_cl, n, H, Wd, timesteps, context, y, T, ca=None):
         """x_cl: act channels-last [n, H, W, 64] (first in_channels used). Returns float32 [n*H*W, 16]-strided buffer
@@ -466,13 +514,15 @@ class VideoUNet(nn.Module):
         self._engine = None
         self._engine_key = None
 
-    # weights may be (re)loaded at any time (init_from_ckpt, EMA swap): repack lazily when any parameter changed
-    def _state_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+    # weights may be (re)loaded at any time (init_from_ckpt, EMA swap through `.data.copy_`): repack lazily when any
+    # parameter changed (weights_key); `invalidate()` forces it for in-place edits the key cannot see
+    def invalidate(self):
+        self._engine, self._engine_key = None, None
 
     def engine(self, device):
-        key = (str(device), self._state_key())
+        key = weights_key(self, device)
         if self._engine is None or self._engine_key != key:
+            self._engine = None                                   # release the old packed weights / workspaces first
             self._engine = UNetEngine(self.cfg, self.state_dict(), device)
             self._engine_key = key
         return self._engine

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops, spec
-from .unet import BufferPool, register_param_tree
+from .unet import BufferPool, register_param_tree, weights_key
 
 
 class DecoderEngine:
@@ -319,11 +319,19 @@ class Encoder(nn.Module):
         register_param_tree(self, spec.encoder_param_shapes(self.cfg))
         self._engines = {}
 
+    def invalidate(self):
+        self._engines = {}
+
     def engine(self, device, post=None, post_key=None):
-        key = (str(device), post_key, tuple((p.data_ptr(), p._version) for p in self.parameters()))
-        if key not in self._engines:
-            self._engines = {key: EncoderEngine(self.cfg, self.state_dict(), device, post=post)}
-        return self._engines[key]
+        """One packed engine per `post` fold (plain forward / encode_mode), at most two kept; a weight change drops them all."""
+        wk = weights_key(self, device)
+        if getattr(self, "_wkey", None) != wk:
+            self._engines, self._wkey = {}, wk
+        if post_key not in self._engines:
+            if len(self._engines) >= 2:
+                self._engines.pop(next(iter(self._engines)))
+            self._engines[post_key] = EncoderEngine(self.cfg, self.state_dict(), device, post=post)
+        return self._engines[post_key]
 
     def _run(self, x, eng):
         if not x.is_cuda:
@@ -348,7 +356,9 @@ class Encoder(nn.Module):
         """scale_factor * mode(DiagonalGaussian(quant_conv(encoder(x)))) = the first z_channels of quant_conv's output."""
         z = self.cfg["z_channels"]
         post = (quant_weight[:z], quant_bias[:z], scale_factor)
-        pk = (quant_weight.data_ptr(), quant_weight._version, quant_bias.data_ptr(), quant_bias._version, float(scale_factor))
+        # keyed on the CONTENT of the (tiny: 2z x 2z) quant_conv so a freshly materialised tensor with the same values hits
+        pk = (tuple(quant_weight.detach().double().flatten().tolist()), tuple(quant_bias.detach().double().flatten().tolist()),
+              float(scale_factor))
         return self._run(x, self.engine(x.device, post=post, post_key=pk))
 
 
@@ -389,9 +399,13 @@ class VideoDecoder(_Base):
     def get_last_layer(self, skip_time_mix=False, **kwargs):
         return self.conv_out.time_mix_conv.weight if not skip_time_mix else self.conv_out.weight
 
+    def invalidate(self):
+        self._engine, self._engine_key = None, None
+
     def engine(self, device):
-        key = (str(device), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        key = weights_key(self, device)
         if self._engine is None or self._engine_key != key:
+            self._engine = None
             self._engine = DecoderEngine(self.cfg, self.state_dict(), device)
             self._engine_key = key
         return self._engine

@@ -208,8 +208,11 @@ class _FakeEngine:
     def __init__(self):
         self.pool = _FakePool()
 
-    def cross_attn_vectors(self, ctx, T):
+    def cross_attn_vectors(self, ctx, T, static=False):
         return ctx[:, 0, :4].clone()
+
+    def forward_graphed(self, x_cl, n, H, W, t_in, ctx, y, T, ca):        # the engine replays a CUDA graph of forward_cl
+        return self.forward_cl(x_cl, n, H, W, t_in, ctx, y, T, ca=ca)
 
     def forward_cl(self, x_cl, n, H, W, t_in, ctx, y, T, ca=None):
         res = torch.zeros(n * H * W, 16)
@@ -326,3 +329,86 @@ def test_bench_reference_arm_json_contract_and_no_cpu_fallback():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+# ------------------------------------------------------------------------------------------- weight (re)load / EMA swap
+def test_engine_key_sees_data_copy_and_litema_shadows_every_parameter():
+    """`param.data.copy_` (what the reference's LitEma.copy_to / restore do, modules/ema.py) does not bump
+    `_version`; the engine cache key must still change, and LitEma must find parameters to shadow (requires_grad)."""
+    from gcd_b200.unet import VideoUNet, weights_key
+    net = VideoUNet(**spec.unet_ctor_kwargs(spec.UNET_TINY))
+    net.load_state_dict(synthetic.seeded_state(spec.unet_param_shapes(spec.UNET_TINY), seed=0))
+    k0 = weights_key(net, "cpu")
+    assert weights_key(net, "cpu") == k0
+    other = synthetic.seeded_state(spec.unet_param_shapes(spec.UNET_TINY), seed=5)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            v = p._version
+            p.data.copy_(other[name])
+            assert p._version == v                      # the blind spot the content probe covers
+    assert weights_key(net, "cpu") != k0
+    n_params = sum(1 for _ in net.parameters())
+    assert all(p.requires_grad for p in net.parameters())
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return
+    ref_shim.install()
+    from sgm.modules.ema import LitEma                 # the reference's own EMA helper
+    ema = LitEma(net, decay=0.999)
+    assert len(ema.m_name2s_name) == n_params           # every weight has a shadow => `model_ema.*` checkpoint keys load
+    k1 = weights_key(net, "cpu")
+    ema.store(net.parameters())
+    for b in ema.buffers():
+        if b.dtype == torch.float32 and b.numel() > 1:
+            b.mul_(0.5)
+    ema.copy_to(net)                                    # ema_scope entry (models/diffusion.py)
+    assert weights_key(net, "cpu") != k1
+    ema.restore(net.parameters())
+    assert weights_key(net, "cpu") == k1
+
+
+def test_embedders_pass_the_general_conditioner_gate():
+    """GeneralConditioner asserts isinstance(embedder, AbstractEmbModel) (encoders/modules.py:93-96). The reference
+    module itself cannot be imported here (open_clip / kornia), so its AbstractEmbModel + GeneralConditioner class sources are
+    cut out with `ast`, installed as `sgm.modules.encoders.modules`, and the repo's embedders are re-imported against it."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    import ast
+    import importlib
+    import types
+    import typing
+    import torch.nn as nn
+    ref_shim.install()
+    path = os.path.join(ref_shim.REF, "sgm", "modules", "encoders", "modules.py")
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("AbstractEmbModel", "GeneralConditioner")]
+    assert len(body) == 2
+    from gcd_b200.sampling import instantiate_from_config
+    ns = {"torch": torch, "nn": nn, "Union": typing.Union, "List": typing.List, "Dict": typing.Dict, "Optional": typing.Optional,
+          "ListConfig": list, "instantiate_from_config": instantiate_from_config, "disabled_train": lambda self, mode=True: self,
+          "count_params": lambda m, verbose=False: 0, "print": lambda *a, **k: None}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    fake = types.ModuleType("sgm.modules.encoders.modules")
+    fake.AbstractEmbModel, fake.GeneralConditioner = ns["AbstractEmbModel"], ns["GeneralConditioner"]
+    pkg = types.ModuleType("sgm.modules.encoders")
+    pkg.__path__ = []
+    saved = {k: sys.modules.get(k) for k in ("sgm.modules.encoders", "sgm.modules.encoders.modules")}
+    sys.modules["sgm.modules.encoders"], sys.modules["sgm.modules.encoders.modules"] = pkg, fake
+    import gcd_b200.embedders as E
+    try:
+        E = importlib.reload(E)
+        assert issubclass(E.ConcatTimestepEmbedderND, fake.AbstractEmbModel)
+        cond = fake.GeneralConditioner([
+            {"target": "gcd_b200.embedders.ConcatTimestepEmbedderND", "params": {"outdim": 256}, "input_key": "fps_id",
+             "is_trainable": False},
+            {"target": "gcd_b200.embedders.SphericalEmbedder", "params": {"embed_dim": 128}, "input_key": "spherical",
+             "is_trainable": False, "ucg_rate": 0.1}])
+        assert [e.input_key for e in cond.embedders] == ["fps_id", "spherical"] and cond.embedders[1].ucg_rate == 0.1
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        importlib.reload(E)
