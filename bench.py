@@ -35,7 +35,8 @@ WORKLOADS = {
     "pardom": dict(unet="UNET_PARDOM", steps=25, max_scale=1.5, name="ParallelDomain-4D gradual RGB, 25-step sample, 14x72x128 latent"),
     "direct50": dict(unet="UNET_KUBRIC", steps=50, max_scale=2.5, name="Kubric-4D direct max180, CFG 2.5, 50-step sample, 14x72x128 latent"),
     # reduced-width network: only for tests of this script's plumbing (tests/test_host_cpu.py), never a reported number
-    "tiny-selftest": dict(unet="UNET_TINY", vae="VAE_TINY", steps=25, max_scale=1.5, name="SELF-TEST ONLY: width-64 network, not a benchmark"),
+    "tiny-selftest": dict(unet="UNET_TINY", vae="VAE_TINY", steps=25, max_scale=1.5, latent=(16, 24),
+                          name="SELF-TEST ONLY: width-64 network at latent 16x24, not a benchmark"),
 }
 
 
@@ -82,12 +83,21 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------ CPU oracle leg
-def cpu_oracle_sample(unet_cfg, vae_cfg, steps, unet_state=None, vae_state=None, sample_hw=(16, 24), vae_hw=(8, 8),
-                      repeats=1):
-    """Times the CPU oracle port (restatement of the reference's PyTorch path) on a bounded sample and extrapolates to
-    the full workload by the exact algorithmic-FLOP ratio. Returns (latent_frames_per_s, description, cores)."""
-    from gcd_b200 import flops, spec, synthetic
+_CPU_CACHE = {}
+
+
+def cpu_oracle_sample(unet_cfg, vae_cfg, steps, unet_state=None, vae_state=None, lat_hw=(LAT_H, LAT_W)):
+    """Times the CPU oracle port (restatement of the reference's PyTorch path, oracle/gcd_oracle.py) on THIS workload's own
+    shapes: ONE CFG UNet forward (28 frames at `lat_hw` = 72x128) and ONE VAE decode of the 14 frames at that size, fp32, after a
+    small warm-up call (thread pool / allocator). One clip = `steps` such forwards + one decode; every sampler step runs the
+    identical network on identically shaped inputs, so clip time = steps x t_forward + t_decode ("extrapolated from 1 step":
+    a full 25-step clip is ~1 h of host time). The same routine serves `cpu_baseline` and `--impl reference`, so the two legs
+    agree by construction. Returns (latent_frames_per_s, description, cores, seconds_measured)."""
+    from gcd_b200 import spec, synthetic
     from oracle import gcd_oracle as O
+    key = (tuple(sorted((k, str(v)) for k, v in unet_cfg.items())), tuple(sorted((k, str(v)) for k, v in vae_cfg.items())), steps, lat_hw)
+    if key in _CPU_CACHE:
+        return _CPU_CACHE[key]
     # Measured on the pool's 128-vCPU B200 hosts (tools/cpu_threads.py, same UNet sample): 16 threads 1.9 s, 32 threads
     # 2.1 s, 64 threads 3.9 s, 128 threads 121 s (the cgroup quota is far below 128 cores) -> use the fastest setting.
     cores = min(os.cpu_count() or 1, 32)
@@ -96,30 +106,34 @@ def cpu_oracle_sample(unet_cfg, vae_cfg, steps, unet_state=None, vae_state=None,
         unet_state = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
     if vae_state is None:
         vae_state = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
-    h, w = sample_hw
-    x, c, uc, ioi = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, h, w)
     n = 2 * T_FRAMES
-    xin = torch.cat((torch.cat([x, x]), torch.cat((uc["concat"], c["concat"]))), 1)
-    ctx = torch.cat((uc["crossattn"], c["crossattn"]))
-    y = torch.cat((uc["vector"], c["vector"]))
+
+    def inputs(h, w):
+        x, c, uc, ioi = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, h, w)
+        xin = torch.cat((torch.cat([x, x]), torch.cat((uc["concat"], c["concat"]))), 1)
+        return xin, torch.cat((uc["crossattn"], c["crossattn"])), torch.cat((uc["vector"], c["vector"])), ioi
+
     t = torch.full((n,), 0.5756)
-    z = torch.randn(T_FRAMES, 4, *vae_hw)
-    tu = tv = 1e30
     with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            O.unet_forward(unet_state, unet_cfg, xin, t, ctx, y, T_FRAMES, ioi)
-            tu = min(tu, time.perf_counter() - t0)
-            t0 = time.perf_counter()
-            O.decode_first_stage(vae_state, vae_cfg, z, T_FRAMES)
-            tv = min(tv, time.perf_counter() - t0)
-    ru = flops.unet_forward_flops(unet_cfg, n, LAT_H, LAT_W) / flops.unet_forward_flops(unet_cfg, n, h, w)
-    rv = flops.decoder_flops(vae_cfg, T_FRAMES, LAT_H, LAT_W) / flops.decoder_flops(vae_cfg, T_FRAMES, *vae_hw)
-    full_s = steps * tu * ru + tv * rv
-    desc = (f"1 CFG UNet forward (28 frames) at latent {h}x{w} ({tu:.2f} s) + 1 VAE decode of 14 frames at latent "
-            f"{vae_hw[0]}x{vae_hw[1]} ({tv:.2f} s), fp32, {cores} threads; extrapolated to {steps} steps at 72x128 by "
-            f"algorithmic FLOP ratios x{ru:.1f} / x{rv:.1f}")
-    return T_FRAMES / full_s, desc, cores, tu + tv
+        xin, ctx, y, ioi = inputs(8, 8)                                        # warm-up, untimed
+        O.unet_forward(unet_state, unet_cfg, xin, t, ctx, y, T_FRAMES, ioi)
+        O.decode_first_stage(vae_state, vae_cfg, torch.randn(T_FRAMES, 4, 8, 8), T_FRAMES)
+        h, w = lat_hw
+        xin, ctx, y, ioi = inputs(h, w)
+        t0 = time.perf_counter()
+        O.unet_forward(unet_state, unet_cfg, xin, t, ctx, y, T_FRAMES, ioi)
+        tu = time.perf_counter() - t0
+        del xin
+        z = torch.randn(T_FRAMES, 4, h, w)
+        t0 = time.perf_counter()
+        O.decode_first_stage(vae_state, vae_cfg, z, T_FRAMES)
+        tv = time.perf_counter() - t0
+    full_s = steps * tu + tv
+    desc = (f"1 CFG UNet forward (28 frames, latent {h}x{w}: {tu:.1f} s) + 1 VAE decode of 14 frames at latent {h}x{w} "
+            f"({tv:.1f} s), fp32, {cores} threads, measured once after a small warm-up call; clip = {steps} x forward + decode "
+            f"(extrapolated from 1 step: the steps are identical network calls)")
+    _CPU_CACHE[key] = (T_FRAMES / full_s, desc, cores, tu + tv)
+    return _CPU_CACHE[key]
 
 
 def run_reference(args, wl):
@@ -127,25 +141,101 @@ def run_reference(args, wl):
     if rank != 0:
         return
     from gcd_b200 import spec
-    from gcd_b200 import synthetic
     unet_cfg, vae_cfg = getattr(spec, wl["unet"]), getattr(spec, wl.get("vae", "VAE_DECODER"))
-    ust = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
-    vst = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, desc, cores, secs = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], ust, vst, sample_hw=(8, 16), vae_hw=(8, 8))
-        if i >= args.warmup:
-            vals.append((v, secs))
-    v = sum(x[0] for x in vals) / len(vals)
+    lat = tuple(wl.get("latent", (LAT_H, LAT_W)))
+    # measured once (one full-size forward + decode is minutes of host time) and reused for every --warmup/--steps iteration
+    v, desc, cores, secs = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], lat_hw=lat)
     line = {"impl": "reference", "metric": "latent-frames/sec", "value": v, "unit": "latent-frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * T_FRAMES / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded random weights, random latents/conditioning)",
-            "config": {"workload": wl["name"], "impl_note": "CPU port of the reference PyTorch path (oracle/gcd_oracle.py); "
-                       "the reference itself is pure Python under /root/reference and cannot travel to the GPU box"},
+            "config": {"workload": wl["name"], "latent": [T_FRAMES, 4, lat[0], lat[1]], "sampler_steps": wl["steps"],
+                       "measured_once": True,
+                       "impl_note": "CPU port of the reference PyTorch path (oracle/gcd_oracle.py) at the workload's own shapes; "
+                                    "the reference itself is pure Python under /root/reference and cannot travel to the GPU box"},
             "cpu_baseline": {"value": v, "unit": "latent-frames/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "latent-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ extra workloads
+def run_extra_workloads(args, wl, pipe, ust, dev, rank, world, lat, timed, gathered):
+    """BASELINE.json configs 3 and 4 and the single-clip latency mode, measured in the same process right after the main
+    line so the driver's N = 1/2/4/8 runs record them (one clip per rank each, CUDA events, max over ranks):
+      direct50     config 4: Kubric-4D direct max180 — 50 Euler steps, guider max scale 2.5 (pretrained/*.yaml:135), + decode,
+                   clips sharded one per rank + the NCCL gather of the latents;
+      pardom       config 3: ParallelDomain-4D network (no auxiliary embedding), 25 steps + decode, same sharding;
+      cfg_parallel N >= 2: ONE clip on ranks 0 and 1, the CFG pair split across them (EulerEDMSampler.set_cfg_parallel) —
+                   ms per clip and rel-L2 of its latents vs the same clip sampled on one GPU.
+    Not part of `value`. Skipped for the self-test workload and under --no-extra."""
+    import torch.distributed as dist
+    from gcd_b200 import spec, synthetic
+    from gcd_b200.pipeline import GCDHotPath
+    if wl.get("unet") != "UNET_KUBRIC" or args.workload != "kubric":
+        return None
+    LH, LW = lat
+    out = {}
+
+    def clip_inputs(cfg):
+        x0, c, uc, _ = synthetic.seeded_inputs(cfg, 1, T_FRAMES, LH, LW, seed=4321 + rank)
+        return x0.to(dev), {k: v.to(dev) for k, v in c.items()}, {k: v.to(dev) for k, v in uc.items()}
+
+    def one_clip(p, x, c, uc):
+        z = p.sample_latents(x.clone(), c, uc)
+        fr = p.decode_first_stage(z)
+        if world > 1:
+            dist.all_gather(gathered, z.contiguous())
+        return z, fr
+
+    def measure(name, p, cfg, note):
+        x, c, uc = clip_inputs(cfg)
+        one_clip(p, x, c, uc)                                           # warm-up (workspaces, graph capture)
+        ms = timed(lambda: one_clip(p, x, c, uc), 1)
+        out[name] = {"ms_per_clip": round(ms, 1), "latent_frames_per_s": round(world * T_FRAMES / (ms / 1e3), 3),
+                     "clips": world, "config": note}
+
+    # ---- config 4: same network, 50 steps, max scale 2.5
+    p50 = GCDHotPath(pipe.unet_cfg, pipe.vae_cfg, num_steps=50, num_frames=T_FRAMES, max_scale=2.5, device=dev)
+    p50.unet, p50.decoder = pipe.unet, pipe.decoder                     # share the loaded modules (and their packed engines)
+    p50.model.diffusion_model = pipe.unet
+    measure("direct50", p50, pipe.unet_cfg, WORKLOADS["direct50"]["name"])
+    # ---- single-clip latency over 2 GPUs (before the ParDom network replaces nothing: it uses the Kubric modules)
+    if world >= 2:
+        grp = dist.new_group([0, 1])                                    # every rank must take part in group creation
+        if rank < 2:
+            x0, c, uc, _ = synthetic.seeded_inputs(pipe.unet_cfg, 1, T_FRAMES, LH, LW, seed=777)      # the SAME clip on both ranks
+            x, c, uc = x0.to(dev), {k: v.to(dev) for k, v in c.items()}, {k: v.to(dev) for k, v in uc.items()}
+            z_ref = pipe.sample_latents(x.clone(), c, uc)
+            pipe.set_cfg_parallel(grp)
+            pipe.sample_latents(x.clone(), c, uc)                       # warm-up
+            torch.cuda.synchronize()
+            dist.barrier(group=grp)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            z = pipe.sample_latents(x.clone(), c, uc)
+            if rank == 0:
+                pipe.decode_first_stage(z)
+            e1.record()
+            torch.cuda.synchronize()
+            pipe.set_cfg_parallel(None)
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=grp)
+            out["cfg_parallel"] = {"ms_per_clip": round(ms.item(), 1), "gpus": 2,
+                                   "rel_l2_vs_single_gpu_latents": float(((z - z_ref).norm() / z_ref.norm()).item()),
+                                   "config": "one clip, CFG pair split over ranks 0/1, one NCCL all_gather of the network "
+                                             "output per step; 25 steps + decode on rank 0"}
+        dist.barrier()
+    # ---- config 3: ParDom network = the Kubric state without the auxiliary-embedding tensors (seeded per tensor name)
+    pcfg = spec.UNET_PARDOM
+    shapes = spec.unet_param_shapes(pcfg)
+    pst = {k: ust[k] for k in shapes} if ust is not None else synthetic.seeded_state(shapes, seed=0)
+    pp = GCDHotPath(pcfg, pipe.vae_cfg, num_steps=25, num_frames=T_FRAMES, max_scale=1.5, device=dev)
+    pp.unet.load_state_dict(pst, strict=True)
+    pp.unet.to(dev)
+    pp.decoder = pipe.decoder
+    measure("pardom", pp, pcfg, WORKLOADS["pardom"]["name"])
+    del pp
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------ product arm
@@ -158,6 +248,7 @@ def main():
     ap.add_argument("--workload", default="kubric", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads block (BASELINE configs 3/4, CFG-parallel)")
     ap.add_argument("--profile-run", action="store_true",
                     help="for ncu: exactly --warmup/--steps resident steps, no e2e / instrumented / CPU passes, no JSON claims")
     args = ap.parse_args()
@@ -186,17 +277,16 @@ def main():
     ust = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
     vst = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
     pipe.load_state(ust, vst)
-    if world > 1 or args.no_cpu_baseline:
-        ust = vst = None                      # 6 GB of host fp32 weights per rank: only the N=1 CPU-baseline leg reuses them
     # rank r samples its own clip: seed 1234 + r (scripts/test.py:1059-1084 strides examples over workers the same way)
-    x0, c, uc, _ = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, LAT_H, LAT_W, seed=1234 + rank)
+    LH, LW = tuple(wl.get("latent", (LAT_H, LAT_W)))
+    x0, c, uc, _ = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, LH, LW, seed=1234 + rank)
     pin = lambda t: t.pin_memory()
     hx, hc, huc = pin(x0), {k: pin(v) for k, v in c.items()}, {k: pin(v) for k, v in uc.items()}
     dx, dc, duc = x0.to(dev), {k: v.to(dev) for k, v in c.items()}, {k: v.to(dev) for k, v in uc.items()}
     h2d = sum(t.numel() * t.element_size() for t in [hx, *hc.values(), *huc.values()])
-    frames_host = torch.empty(T_FRAMES, 3, LAT_H * 8, LAT_W * 8, dtype=torch.float32).pin_memory()
+    frames_host = torch.empty(T_FRAMES, 3, LH * 8, LW * 8, dtype=torch.float32).pin_memory()
     d2h = frames_host.numel() * 4
-    gathered = [torch.empty(T_FRAMES, 4, LAT_H, LAT_W, device=dev) for _ in range(world)] if world > 1 else None
+    gathered = [torch.empty(T_FRAMES, 4, LH, LW, device=dev) for _ in range(world)] if world > 1 else None
 
     def step_resident(collective=True):
         z = pipe.sample_latents(dx.clone(), dc, duc)
@@ -249,6 +339,8 @@ def main():
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    extra = None if args.no_extra else run_extra_workloads(args, wl, pipe, ust, dev, rank, world, (LH, LW), timed, gathered)
+
     frames_total = world * args.steps * T_FRAMES
     value = frames_total / (ms / 1e3)
     e2e_value = frames_total / (ms_e2e / 1e3)
@@ -263,7 +355,7 @@ def main():
         tc = summ.get("tc_gemm", dict(ms=1e-9, flops=0.0, launches=0))
         tot_ms = sum(d["ms"] for d in summ.values())
         tc_tflops = tc["flops"] / (tc["ms"] / 1e3) / 1e12
-        per_frame = flops.clip_flops(unet_cfg, vae_cfg, T_FRAMES, LAT_H, LAT_W, wl["steps"]) / T_FRAMES
+        per_frame = flops.clip_flops(unet_cfg, vae_cfg, T_FRAMES, LH, LW, wl["steps"]) / T_FRAMES
         path_tflops = per_frame * (value / world) / 1e12
         traffic, traffic_detail = None, None
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
@@ -284,7 +376,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if ops.lib().gcd_act_dtype() == 1 else "f16",
                 "data": "synthetic (seeded random weights of the named architecture, random latents/conditioning)",
-                "config": {"workload": wl["name"], "clips_per_gpu_per_step": 1, "latent": [T_FRAMES, 4, LAT_H, LAT_W],
+                "config": {"workload": wl["name"], "clips_per_gpu_per_step": 1, "latent": [T_FRAMES, 4, LH, LW],
                            "sampler_steps": wl["steps"], "cfg_batch": 2 * T_FRAMES, "decode": not args.no_decode,
                            "parallelism": f"clips x{world} (one NCCL all_gather of latents per step)" if world > 1 else "single GPU",
                            "l2": "no explicit flush: per-step working set (3.2 GB fp16 weights + multi-GB activations) >> 126 MB L2",
@@ -293,8 +385,10 @@ def main():
                         "ms_per_step": round(ms_e2e / args.steps, 2),
                         "api": "gcd_b200.pipeline.GCDHotPath.sample_video(pinned host noise/cond) + frames -> pinned host"},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
-        if world == 1 and not args.no_cpu_baseline:
-            v, desc, cores, _ = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], ust, vst)
+        if extra:
+            line["extra_workloads"] = extra
+        if world == 1 and not args.no_cpu_baseline and not args.profile_run:
+            v, desc, cores, _ = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], ust, vst, lat_hw=tuple(wl.get("latent", (LAT_H, LAT_W))))
             line["cpu_baseline"] = {"value": v, "unit": "latent-frames/s", "cores": cores, "kind": "port", "sample": desc}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -332,23 +332,32 @@ __device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
     return d;
 }
 
-// GEGLU gate for a pair: returns (v0 * gelu(g0), v1 * gelu(g1)) with gelu(g) = g * Phi(g) (torch F.gelu, erf form).
-// Phi(g) - 1/2 = g * Q(g^2) on |g| <= 4 with a degree-7 minimax polynomial Q (max abs error of Phi 2.3e-5, tail beyond
-// |g| = 4 clamped: 3.2e-5) — no MUFU, 7 FFMA2 per pair. The previous erff / rcp+ex2 forms made the K=320 GEGLU GEMMs
-// MUFU- and issue-bound (profiles/r1_notes.md). Absolute error of the result <= 1.3e-4 * |v|, below the 16-bit
-// rounding of the output for the activation ranges of the network.
-__device__ __forceinline__ uint64_t geglu_pair(uint64_t v, float g0, float g1) {
+__device__ __forceinline__ uint64_t add2f(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// GEGLU gate for a pair: returns (v0 * gelu(g0), v1 * gelu(g1)) with gelu(g) = g * Phi(g) (torch F.gelu, erf form;
+// gcd-model/sgm/modules/attention.py:87-94). Phi(g) - 1/2 = g * Q(g^2) on |g| <= 4 with a degree-6 minimax polynomial Q
+// (max abs error of Phi 1.05e-4, fitted in tools/fit_gelu.py; the tail beyond |g| = 4 is clamped: 3.2e-5) — no MUFU,
+// 6 FFMA2 + 2 FMNMX per value pair. The previous erff / rcp+ex2 forms made the K=320 GEGLU GEMMs MUFU- and issue-bound
+// (profiles/r1_notes.md §1), the degree-7 fit of round 1 (2.4e-5) cost one more FFMA2 per pair in an epilogue that ncu shows
+// issue/latency-bound (profiles/r2_notes.md §1). Absolute error of the result <= 4.2e-4 * |v| at |g| = 4 and <= 1.05e-4 * |g v|
+// in general — a fifth of the 16-bit rounding (2^-11 relative) of the stored output.
+__device__ __forceinline__ uint64_t geglu_pair(uint64_t v, uint64_t g) {
+    float g0, g1;
+    upk2f(g, g0, g1);
     const float l0 = fmaxf(g0, -4.0f), l1 = fmaxf(g1, -4.0f);        // multiplier: max(g, -4) bounds the far-tail error
     const uint64_t gl = pk2f(l0, l1);
     const uint64_t gc = pk2f(fminf(l0, 4.0f), fminf(l1, 4.0f));
     const uint64_t u = mul2f(gc, gc);
-    uint64_t q = fma2f(u, pk2f(-1.5810971e-9f, -1.5810971e-9f), pk2f(1.2172849e-7f, 1.2172849e-7f));
-    q = fma2f(q, u, pk2f(-4.1012522e-6f, -4.1012522e-6f));
-    q = fma2f(q, u, pk2f(8.0671714e-5f, 8.0671714e-5f));
-    q = fma2f(q, u, pk2f(-1.0482300e-3f, -1.0482300e-3f));
-    q = fma2f(q, u, pk2f(9.6649509e-3f, 9.6649509e-3f));
-    q = fma2f(q, u, pk2f(-6.6175476e-2f, -6.6175476e-2f));
-    q = fma2f(q, u, pk2f(3.9884755e-1f, 3.9884755e-1f));
+    uint64_t q = fma2f(u, pk2f(2.816124126e-8f, 2.816124126e-8f), pk2f(-1.891901693e-6f, -1.891901693e-6f));
+    q = fma2f(q, u, pk2f(5.419063147e-5f, 5.419063147e-5f));
+    q = fma2f(q, u, pk2f(-8.789830441e-4f, -8.789830441e-4f));
+    q = fma2f(q, u, pk2f(9.112960568e-3f, 9.112960568e-3f));
+    q = fma2f(q, u, pk2f(-6.538837149e-2f, -6.538837149e-2f));
+    q = fma2f(q, u, pk2f(3.985269200e-1f, 3.985269200e-1f));
     const uint64_t phi = fma2f(gc, q, pk2f(0.5f, 0.5f));
     return mul2f(v, mul2f(gl, phi));
 }

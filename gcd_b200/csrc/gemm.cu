@@ -154,8 +154,14 @@ __device__ __forceinline__ void add_residual_row(float* xf, const uint8_t* base,
 // KC = 64-wide K chunks per pipeline stage: 2 for narrow tiles (BN <= 160), whose 4 MMAs per chunk (320 cycles) are
 // shorter than the issuing thread's per-stage overhead (mbarrier wait + fence + commit) — measured: BN=160 tiles
 // plateaued at 1.12 PFLOP/s in every mode while BN=256 reached 1.45-1.54 (tools/bench_convgemm.py).
-template <int BN, int MODE, int KC>
-__global__ void __launch_bounds__(384, 1)
+// NWG = epilogue warpgroups (2 or 3; 128 + 128*NWG threads). The accumulator column SPANS of the tile stream are dealt
+// round-robin to the warpgroups ACROSS tiles (span number G_k + s of the CTA's k-th tile goes to warpgroup (G_k + s) % NWG), so
+// every warpgroup stays busy whatever the number of spans per tile (GEGLU tiles have two). ncu on the K=320 GEGLU GEMM
+// (profiles/r2_notes.md §1): issue slots 46 %, tensor pipe 40 %, each epilogue warp issuing only 20 % of the time (fixed-latency
+// dependency stalls) — the epilogue was latency-bound with two warps per scheduler; NWG = 3 puts three there. With NWG = 3 the
+// register file is re-split with setmaxnreg (producer / MMA / allocator warps 56, epilogue warps 152).
+template <int BN, int MODE, int KC, int NWG>
+__global__ void __launch_bounds__(128 + 128 * NWG, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2,
                const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapR2, const TcParams p) {
@@ -169,18 +175,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint8_t* sB = sA + STAGES * KC * TC_A_BYTES;           // [STAGES][KC][B_BYTES]
     const int OT = 16384;                                             // bytes of one output staging tile (128 x 128 B)
     const int RT1 = p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0, RT2 = p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0;
-    uint8_t* sO = sB + STAGES * KC * B_BYTES;               // [2 warpgroups][obufs] output staging
-    uint8_t* sR1 = sO + 2 * p.obufs * OT;                   // [2 warpgroups][rbufs] residual 1 (if any)
-    uint8_t* sR2 = sR1 + 2 * p.rbufs * RT1;                 // [2 warpgroups][rbufs] residual 2 (if any)
-    float* sBias = reinterpret_cast<float*>(sR2 + 2 * p.rbufs * RT2); // [2][256] bias slice of the current tile, per warpgroup
-    float* sStat = sBias + 512;             // [8 epilogue warps][32 groups][sum, sum of squares] (gn_acc only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (p.gn_acc ? 512 : 0));
+    uint8_t* sO = sB + STAGES * KC * B_BYTES;               // [NWG warpgroups][obufs] output staging
+    uint8_t* sR1 = sO + NWG * p.obufs * OT;                 // [NWG warpgroups][rbufs] residual 1 (if any)
+    uint8_t* sR2 = sR1 + NWG * p.rbufs * RT1;               // [NWG warpgroups][rbufs] residual 2 (if any)
+    float* sBias = reinterpret_cast<float*>(sR2 + NWG * p.rbufs * RT2); // [NWG][256] bias slice of the current tile, per warpgroup
+    float* sStat = sBias + NWG * 256;       // [4*NWG epilogue warps][32 groups][sum, sum of squares] (gn_acc only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (p.gn_acc ? NWG * 256 : 0));
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + 8;            // [STAGES]  (STAGES <= 8)
     uint64_t* tfull = bars + 16;           // [2]
     uint64_t* tempty = bars + 18;          // [2]
-    uint64_t* rfull = bars + 20;           // [2 warpgroups][2] residual tiles landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* rfull = bars + 20;           // [NWG warpgroups][2] residual tiles landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + 2 * NWG);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -198,9 +204,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], PAIR ? 512 : 256);   // PAIR: the leader's MMA waits for both CTAs' epilogues
-            mbar_init(&rfull[2 * i], 1); mbar_init(&rfull[2 * i + 1], 1);
+            mbar_init(&tempty[i], (PAIR ? 2 : 1) * 128 * NWG);   // PAIR: the leader's MMA waits for both CTAs' epilogues
         }
+        for (int i = 0; i < 2 * NWG; i++) mbar_init(&rfull[i], 1);
         fence_barrier_init();
     }
     if (warp == 2) { if (PAIR) tmem_alloc_2cta(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
@@ -218,6 +224,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int TW = 1 << p.lTW, TH = 1 << p.lTH;
     const int TN = 128 >> (p.lTW + p.lTH);
 
+    if (warp < 4) {
+    // NWG == 3 (512 threads): 4 x 32 x 56 + 12 x 32 x 152 = 65 536 registers. Each role's code sits in the same branch as its
+    // setmaxnreg so that ptxas allocates that region against the new limit.
+    if (NWG == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
@@ -300,9 +310,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (PAIR) umma_commit_2cta_mc(&tfull[as], (uint16_t)0x3); else umma_commit(&tfull[as]);
             }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue: two warpgroups, alternating 32-column chunks =====================
-        const int g = (warp - 4) >> 2;              // epilogue warpgroup 0 / 1 (own staging buffers, own named barrier)
+    }
+    } else {
+        if (NWG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        // ===================== epilogue: NWG warpgroups, spans dealt round-robin across the CTA's tile stream =====================
+        const int g = (warp - 4) >> 2;              // epilogue warpgroup (own staging buffers, own named barrier)
         const int q = warp & 3;                     // TMEM lane quadrant of this warp
         const int r = q * 32 + lane;                // tile row of this thread (= TMEM lane)
         const bool leader = ((threadIdx.x & 127) == 0);   // issues this warpgroup's TMA loads / stores
@@ -314,55 +326,61 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint32_t pfc = 0;                           // residual chunks prefetched by this warpgroup's leader
         float* myBias = sBias + g * 256;
         const int bar_id = 1 + g;
+        constexpr int BAR_ALL = NWG + 1;            // named barrier of all epilogue threads (statistics flush)
+        // One span = one staging tile = one TMA store with 128-byte rows whenever possible (32 fp32 / 64 fp16 / 64 GEGLU output
+        // columns). Narrow-row stores made the TMA store engine the bottleneck of the K=320 GEMMs (profiles/r1_notes.md §1, v6).
+        const int span = p.of32 ? 32 : (p.geglu ? 128 : 64);
+        auto nspans = [&](int tile) { return (min(BN, p.N - (tile % p.n_tiles) * BN) + span - 1) / span; };
 
-        // residual prefetcher (leader only): walks this warpgroup's (tile, span, chunk) sequence one chunk ahead
-        const int pspan = p.of32 ? 32 : (p.geglu ? 128 : 64);
-        int pf_tile = tile0, pf_s0 = g * pspan, pf_cc = 0;
+        // residual prefetcher (leader only): walks this warpgroup's (tile, span, chunk) sequence one chunk ahead.
+        // pf_G = spans of the CTA's earlier tiles mod NWG; span pf_s of pf_tile is mine iff (pf_G + pf_s) % NWG == g.
+        int pf_tile = tile0, pf_G = 0, pf_s = g, pf_cc = 0;
         auto prefetch_residual = [&]() {
-            while (pf_tile < total) {                                  // skip tiles where this warpgroup has no span
-                const int nt = pf_tile % p.n_tiles;
-                if (pf_s0 < BN && nt * BN + pf_s0 < p.N) break;
-                pf_s0 = g * pspan; pf_cc = 0; pf_tile += tile_step;
+            while (pf_tile < total) {                                  // skip tiles where this warpgroup has no span (left)
+                const int ns = nspans(pf_tile);
+                if (pf_s < ns) break;
+                pf_G = (pf_G + ns) % NWG; pf_tile += tile_step; pf_s = (g + NWG - pf_G) % NWG; pf_cc = 0;
             }
             if (pf_tile >= total) return;
             const int nt = pf_tile % p.n_tiles, mt = (pf_tile / p.n_tiles) * CL + crank;
             const int tx = mt % p.ntx, ty = (mt / p.ntx) % p.nty, tz = mt / (p.ntx * p.nty);
-            const int ncol = nt * BN + pf_s0 + pf_cc;
+            const int s0 = pf_s * span;
+            const int ncol = nt * BN + s0 + pf_cc;
             const uint32_t pb = p.rbufs == 2 ? (pfc & 1) : 0;
             pfc++;
             mbar_expect_tx(&rfull[2 * g + pb], rbytes);
             if (p.has_r1) tma_load_4d(&mapR1, myR1 + pb * RT1, &rfull[2 * g + pb], ncol, tx * TW, ty * TH, tz * TN);
             if (p.has_r2) tma_load_4d(&mapR2, myR2 + pb * RT2, &rfull[2 * g + pb], ncol, tx * TW, ty * TH, tz * TN);
-            const int width = min(pspan, min(BN - pf_s0, p.N - nt * BN - pf_s0));
+            const int width = min(span, min(BN - s0, p.N - nt * BN - s0));
             pf_cc += 32;
-            if (pf_cc >= width) { pf_cc = 0; pf_s0 += 2 * pspan; }
+            if (pf_cc >= width) { pf_cc = 0; pf_s += NWG; }
         };
         // with rbufs == 2 two residual chunks are always in flight per warpgroup: with one, each SM had at most 32 KB of loads
         // outstanding (148 SMs x 32 KB / ~1.5 us HBM latency ~ 3.2 TB/s) — the measured ceiling of the fp32-residual linears
         if (leader && has_res) { prefetch_residual(); if (p.rbufs == 2) prefetch_residual(); }
 
         uint32_t ci = 0, rc = 0;                    // spans / residual chunks processed by this warpgroup
-        int it = 0;
+        int it = 0, G = 0;
         // gn_acc: many consecutive tiles of this CTA lie in the same image (VAE: 14 frames or ONE clip over 64 512 tiles),
         // where per-tile global fp64 atomics serialise on 64 addresses in L2 (measured: 2.7 -> 5-6 ms per full-resolution
         // conv). Each epilogue warp then sums into its own shared-memory table (plain adds in a fixed order: deterministic)
-        // and the CTA flushes the eight tables with fp64 atomics when the image changes.
+        // and the CTA flushes the tables with fp64 atomics when the image changes.
         int cur_img = -1;
         float* myStat = sStat + (warp - 4) * 64;
         auto flush_stats = [&]() {
-            named_bar_sync(3, 256);                                // both warpgroups' adds for cur_img are done
+            named_bar_sync(BAR_ALL, 128 * NWG);                    // all warpgroups' adds for cur_img are done
             if (g == 0 && (threadIdx.x & 127) < 64) {
                 const int i = threadIdx.x & 127;
                 double v = 0.0;
 #pragma unroll
-                for (int w = 0; w < 8; w++) { v += (double)sStat[w * 64 + i]; sStat[w * 64 + i] = 0.f; }
+                for (int w = 0; w < 4 * NWG; w++) { v += (double)sStat[w * 64 + i]; sStat[w * 64 + i] = 0.f; }
                 if (v != 0.0) atomicAdd(p.gn_stats + (int64_t)cur_img * p.gn_groups * 2 + i, v);
             }
-            named_bar_sync(3, 256);
+            named_bar_sync(BAR_ALL, 128 * NWG);
         };
         if (p.gn_acc) {
             myStat[lane] = 0.f; myStat[lane + 32] = 0.f;
-            named_bar_sync(3, 256);
+            named_bar_sync(BAR_ALL, 128 * NWG);
         }
         for (int tile = tile0; tile < total; tile += tile_step, it++) {
             const int as = it & 1;
@@ -373,6 +391,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int ty = (mt / p.ntx) % p.nty;
             const int tz = mt / (p.ntx * p.nty);
             const int n0 = nt * BN;
+            const int ns = nspans(tile);
+            const int s_first = (g + NWG - G) % NWG;             // my first span of this tile (>= ns: none)
+            G = (G + ns) % NWG;
             if (p.gn_acc && mt < m_tiles) {
                 const int64_t row0 = ((int64_t)(tz * TN) * p.Yo + ty * TH) * p.Xo + tx * TW;
                 const int img = (int)(row0 / p.gn_rpi);
@@ -382,25 +403,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
             const float* rv = nullptr;
-            if (p.rowvec) {
-                const int x = tx * TW + (r & (TW - 1));
-                const int y = ty * TH + ((r >> p.lTW) & (TH - 1));
-                const int z = tz * TN + (r >> (p.lTW + p.lTH));
-                if (x < p.Xo && y < p.Yo && z < p.Zo)
-                    rv = p.rowvec + ((((int64_t)z * p.Yo + y) * p.Xo + x) / p.rpv) * (int64_t)p.ldv;
+            if (s_first < ns) {
+                // per-row vector (emb_layers add / len-1 cross-attention bias): when every row of the tile reads the SAME vector
+                // (a tile inside one frame / clip — always, for the UNet's shapes) it is folded into the staged bias slice
+                const float* rv_tile = nullptr;
+                if (p.rowvec) {
+                    const int x0 = tx * TW, y0 = ty * TH, z0 = tz * TN;
+                    if (x0 < p.Xo && y0 < p.Yo && z0 < p.Zo) {
+                        const int x1 = min(x0 + TW, p.Xo) - 1, y1 = min(y0 + TH, p.Yo) - 1, z1 = min(z0 + TN, p.Zo) - 1;
+                        const int64_t i0 = (((int64_t)z0 * p.Yo + y0) * p.Xo + x0) / p.rpv, i1 = (((int64_t)z1 * p.Yo + y1) * p.Xo + x1) / p.rpv;
+                        if (i0 == i1) rv_tile = p.rowvec + i0 * (int64_t)p.ldv;
+                    }
+                    if (!rv_tile) {
+                        const int x = x0 + (r & (TW - 1));
+                        const int y = y0 + ((r >> p.lTW) & (TH - 1));
+                        const int z = z0 + (r >> (p.lTW + p.lTH));
+                        if (x < p.Xo && y < p.Yo && z < p.Zo)
+                            rv = p.rowvec + ((((int64_t)z * p.Yo + y) * p.Xo + x) / p.rpv) * (int64_t)p.ldv;
+                    }
+                }
+                for (int j = threadIdx.x & 127; j < BN; j += 128) {
+                    float b = 0.f;
+                    if (n0 + j < p.N) {
+                        if (p.bias) b = __ldg(p.bias + n0 + j);
+                        if (rv_tile) b += __ldg(rv_tile + n0 + j);
+                    }
+                    myBias[j] = b;
+                }
+                named_bar_sync(bar_id, 128);                  // B0: bias slice staged (the previous tile's reads ended at its last B2)
             }
-            for (int j = threadIdx.x & 127; j < BN; j += 128)
-                myBias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-            named_bar_sync(bar_id, 128);                      // B0: bias slice staged (also orders it after the previous tile's reads)
+            // also taken without a span in this tile: arriving on tempty below is only legal once the accumulator's previous
+            // phase is over, which tfull of THIS tile implies (the MMA waited for it)
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
-            // Each warpgroup owns alternating column SPANS of the tile; one span = one staging tile = one TMA store with
-            // 128-byte rows whenever possible (32 fp32 / 64 fp16 / 64 GEGLU output columns). Narrow-row stores made the
-            // TMA store engine the bottleneck of the K=320 GEMMs (profiles/r1_notes.md §1, v6).
-            const int span = p.of32 ? 32 : (p.geglu ? 128 : 64);
 #pragma unroll 1
-            for (int s0 = g * span; s0 < BN && n0 + s0 < p.N; s0 += 2 * span, ci++) {
+            for (int si = s_first; si < ns; si += NWG, ci++) {
+                const int s0 = si * span;
                 uint8_t* myO = myObase + (p.obufs == 2 ? (ci & 1) * OT : 0);
                 const int width = min(span, min(BN - s0, p.N - n0 - s0));      // accumulator columns in this span
                 const bool wide = p.of32 || p.geglu || width > 32;             // 128-byte staging rows (SWIZZLE_128B)
@@ -414,36 +453,48 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
-                    float xf[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) xf[j] = __uint_as_float(v[j]);
                     const int n = n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {                          // bias slice from smem (warp-broadcast reads)
-                        const float4 t = *reinterpret_cast<const float4*>(myBias + c0 + j);
-                        xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
-                    }
-                    if (rv) {
+                    if (rv) {                                                  // rows of this tile read different vectors (rare)
                         if (n + 32 <= p.N) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 t = __ldg(reinterpret_cast<const float4*>(rv + n + j));
-                                xf[j] += t.x; xf[j + 1] += t.y; xf[j + 2] += t.z; xf[j + 3] += t.w;
+                                v[j] = __float_as_uint(__uint_as_float(v[j]) + t.x); v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + t.y);
+                                v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + t.z); v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + t.w);
                             }
                         } else {                                               // ragged N tail
 #pragma unroll 1
                             for (int j = 0; j < p.N - n; j++) {
                                 const float add = rv[n + j];
 #pragma unroll
-                                for (int k = 0; k < 32; k++) if (k == j) xf[k] += add;
+                                for (int k = 0; k < 32; k++) if (k == j) v[k] = __float_as_uint(__uint_as_float(v[k]) + add);
                             }
                         }
                     }
-                    if (p.geglu) {
+                    uint64_t x2[16];                                           // accumulator + bias, packed fp32 pairs (FADD2)
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2)
-                            upk2f(geglu_pair(pk2f(xf[j], xf[j + 1]), xf[16 + j], xf[17 + j]), xf[j], xf[j + 1]);
+                    for (int j = 0; j < 16; j += 2) {                          // bias slice from smem (warp-broadcast reads)
+                        const float4 t = *reinterpret_cast<const float4*>(myBias + c0 + 2 * j);
+                        x2[j] = add2f(pk2f(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), pk2f(t.x, t.y));
+                        x2[j + 1] = add2f(pk2f(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), pk2f(t.z, t.w));
                     }
+                    if (p.geglu) {                             // value columns 0..15, gate columns 16..31 -> 16 outputs of a 128-byte row
+                        uint32_t pw[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float o0, o1;
+                            upk2f(geglu_pair(x2[j], x2[8 + j]), o0, o1);
+                            pw[j] = pack2(o0, o1);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 2; c++)
+                            *reinterpret_cast<uint4*>(myO + stg_off(r, (cc >> 5) * 2 + c, 8, 0)) =
+                                make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
+                        continue;
+                    }
+                    float xf[32];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) upk2f(x2[j], xf[2 * j], xf[2 * j + 1]);
                     if (p.act == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) xf[j] = silu(xf[j]);
@@ -469,12 +520,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             *reinterpret_cast<uint4*>(myO + stg_off(r, c, 8, 0)) =
                                 make_uint4(__float_as_uint(xf[4 * c]), __float_as_uint(xf[4 * c + 1]),
                                            __float_as_uint(xf[4 * c + 2]), __float_as_uint(xf[4 * c + 3]));
-                    } else if (p.geglu) {                      // 16 output columns of a 64-column (128-byte) row
-#pragma unroll
-                        for (int c = 0; c < 2; c++)
-                            *reinterpret_cast<uint4*>(myO + stg_off(r, (cc >> 5) * 2 + c, 8, 0)) =
-                                make_uint4(pack2(xf[8 * c], xf[8 * c + 1]), pack2(xf[8 * c + 2], xf[8 * c + 3]),
-                                           pack2(xf[8 * c + 4], xf[8 * c + 5]), pack2(xf[8 * c + 6], xf[8 * c + 7]));
                     } else {                                   // 32 output columns: half of a 128-byte row, or a 64-byte row
 #pragma unroll
                         for (int c = 0; c < 4; c++)
@@ -554,7 +599,8 @@ static int ilog2(int v) {
     return l;
 }
 
-template <int BN, int MODE>
+constexpr int TC_RETRY_NWG2 = 77;
+template <int BN, int MODE, int NWG>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mO2,
                      const CUtensorMap& mR1, const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
     static bool configured = false;
@@ -565,7 +611,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     constexpr int KC = (BN <= 160 && MODE == 3) ? 2 : 1;
     constexpr int STAGE_BYTES = KC * (TC_A_BYTES + (MODE == 3 ? BN * 64 : BN * 128));
     if (!configured) {
-        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, KC, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         int dev = 0;
         GCD_CUDA_CHECK(cudaGetDevice(&dev));
         GCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -577,27 +623,29 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     // short K loop => the epilogue is the critical path: double-buffer its staging tiles if >= 3 pipeline stages remain
     auto plan = [&](int fixed, int& obufs, int& stages) {
         // short K loop: first keep two residual chunks in flight (HBM latency), then double-buffer the output staging
-        p.rbufs = (RT > 0 && kiters <= 24 && (TC_SMEM_MAX - (2 * OT + 4 * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
-        obufs = (kiters <= 24 && (TC_SMEM_MAX - (4 * OT + 2 * p.rbufs * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
-        stages = (TC_SMEM_MAX - (2 * obufs * OT + 2 * p.rbufs * RT + fixed) - 256) / STAGE_BYTES;
+        p.rbufs = (RT > 0 && kiters <= 24 && (TC_SMEM_MAX - (NWG * OT + 2 * NWG * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
+        obufs = (kiters <= 24 && (TC_SMEM_MAX - (2 * NWG * OT + NWG * p.rbufs * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
+        stages = (TC_SMEM_MAX - (NWG * obufs * OT + NWG * p.rbufs * RT + fixed) - 256) / STAGE_BYTES;
         if (stages > 8) stages = 8;
     };
-    int fixed = 2048 /*bias*/, stages;
+    p.gn_acc = 0;
+    int fixed = NWG * 1024 /*bias slices*/, stages;
     plan(fixed, p.obufs, stages);
     if (p.gn_stats) {
         // consecutive tiles of a CTA are num_sms M-tiles apart: accumulate per CTA when an image spans many such strides ...
         const int64_t rows = (int64_t)p.Xo * p.Yo * p.Zo;
         const int64_t n_img = (rows + p.gn_rpi - 1) / p.gn_rpi;
         int ob2, st2;
-        plan(fixed + 2048, ob2, st2);
+        plan(fixed + NWG * 1024, ob2, st2);
         // ... unless the 2 KB of tables would leave fewer than 4 pipeline stages (then keep the direct global atomics)
         if (p.gn_groups == 32 && (int64_t)p.ntx * p.nty * p.ntz / n_img >= 4 * (int64_t)num_sms && ob2 == p.obufs && (st2 == stages || st2 >= 4)) {
             p.gn_acc = 1;
-            fixed += 2048;
+            fixed += NWG * 1024;
         }
         plan(fixed, p.obufs, stages);          // final plan (also restores rbufs when the tables were rejected)
     }
-    const int epi = 2 * p.obufs * OT + 2 * p.rbufs * RT + fixed;
+    const int epi = NWG * p.obufs * OT + NWG * p.rbufs * RT + fixed;
+    if (NWG == 3 && stages < 3) return TC_RETRY_NWG2;      // the third warpgroup's staging tiles would starve the operand pipeline
     GCD_REQUIRE(stages >= 2, "tc_gemm: not enough shared memory for the pipeline (BN=%d)", BN);
     p.stages = stages;
     const int smem = stages * STAGE_BYTES + epi + 256;
@@ -608,7 +656,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(384);
+    cfg.blockDim = dim3(128 + 128 * NWG);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -616,7 +664,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GCD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, KC>, mA, mB, mO, mO2, mR1, mR2, p));
+    GCD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, KC, NWG>, mA, mB, mO, mO2, mR1, mR2, p));
     g_launches++;
     return 0;
 }
@@ -643,8 +691,8 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     GCD_REQUIRE(((uintptr_t)op->A & 15) == 0 && ((uintptr_t)op->W & 15) == 0, "gcd_tc_run: operands must be 16B aligned");
     GCD_REQUIRE(op->in_mul == 1 || op->in_mul == 2, "gcd_tc_run: in_mul must be 1 or 2");
     const gcd_epilogue& e = op->ep;
-    GCD_REQUIRE(!e.geglu || (op->N % 256 == 0 && !e.out_f32 && !e.res1 && !e.res2),
-                "gcd_tc_run: GEGLU needs N %% 256 == 0, 16-bit output and no residual");
+    GCD_REQUIRE(!e.geglu || (op->N % 256 == 0 && !e.out_f32 && !e.res1 && !e.res2 && e.a_acc == 1.0f && !e.act),
+                "gcd_tc_run: GEGLU needs N %% 256 == 0, 16-bit output, no residual / scale / activation");
     GCD_REQUIRE(!e.rowvec || e.rows_per_vec > 0, "gcd_tc_run: rows_per_vec must be > 0");
     GCD_REQUIRE(!e.bias || ((uintptr_t)e.bias & 15) == 0, "gcd_tc_run: bias must be 16B aligned");
     GCD_REQUIRE(!e.rowvec || (((uintptr_t)e.rowvec & 15) == 0 && e.ld_rowvec % 4 == 0),
@@ -758,17 +806,25 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
             if (rc) return rc;
         }
     }
-    int rc;
+    // epilogue warpgroups: 2. Three (GCD_TC_NWG=3, experiments) measured 1-20 % SLOWER on every shape of tools/bench_ops.py
+    // (profiles/r2_notes.md §1): the third set of staging tiles costs pipeline stages and the 512-thread launch bound caps the
+    // epilogue at 128 registers, which serialises its eight independent polynomial chains.
+    static const int nwg_env = [] { const char* e = getenv("GCD_TC_NWG"); return e ? atoi(e) : 2; }();
+    const int NWG = nwg_env == 3 ? 3 : 2;
+    int rc = 0;
+#define TC_GO(B, M) ((NWG == 3 && (rc = launch_tc<B, M, 3>(mA, mB, mO, mO2, mR1, mR2, p, st)) != TC_RETRY_NWG2) ? rc \
+                     : launch_tc<B, M, 2>(mA, mB, mO, mO2, mR1, mR2, p, st))
     switch (BN * 10 + MODE) {
-        case 2563: rc = launch_tc<256, 3>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 1603: rc = launch_tc<160, 3>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 1283: rc = launch_tc<128, 3>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 2562: rc = launch_tc<256, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 1602: rc = launch_tc<160, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 1282: rc = launch_tc<128, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 2561: rc = launch_tc<256, 1>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        case 1601: rc = launch_tc<160, 1>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
-        default: rc = launch_tc<128, 1>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
+        case 2563: rc = TC_GO(256, 3); break;
+        case 1603: rc = TC_GO(160, 3); break;
+        case 1283: rc = TC_GO(128, 3); break;
+        case 2562: rc = TC_GO(256, 2); break;
+        case 1602: rc = TC_GO(160, 2); break;
+        case 1282: rc = TC_GO(128, 2); break;
+        case 2561: rc = TC_GO(256, 1); break;
+        case 1601: rc = TC_GO(160, 1); break;
+        default: rc = TC_GO(128, 1); break;
     }
+#undef TC_GO
     return rc ? rc : stats_skipped;
 }

@@ -205,7 +205,8 @@ def conv_t3(x, w, ep):
 
 # ------------------------------------------------------------------------------------------------ norms
 def zero_stats(stats, n_img, groups=32):
-    check(lib().gcd_memset_async(_p(stats), 0, n_img * groups * 2 * 8, _stream()), "memset")
+    with _timed("elem", 0.0, n_img * groups * 2 * 8):
+        check(lib().gcd_memset_async(_p(stats), 0, n_img * groups * 2 * 8, _stream()), "memset")
 
 
 def groupnorm(x, n_img, rows, C, gamma, beta, eps, silu, out, stats, groups=32, have_stats=False):
@@ -241,7 +242,8 @@ def softmax_rows(x, scale, out):
     _need_cuda(x, out)
     rows, cols = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
-    check(lib().gcd_softmax_rows(_p(x), rows, cols, float(scale), _p(out), _stream()), "softmax_rows")
+    with _timed("elem", 0.0, rows * cols * 10):
+        check(lib().gcd_softmax_rows(_p(x), rows, cols, float(scale), _p(out), _stream()), "softmax_rows")
 
 
 # ------------------------------------------------------------------------------------------------ attention
@@ -263,12 +265,14 @@ def attention_temporal(qkv, clips, T, tokens, heads, out):
 def cast_to_act(x, out):
     _need_cuda(x, out)
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
-    check(lib().gcd_cast_f32_to_act(_p(x), x.numel(), _p(out), _stream()), "cast")
+    with _timed("elem", 0.0, x.numel() * 6):
+        check(lib().gcd_cast_f32_to_act(_p(x), x.numel(), _p(out), _stream()), "cast")
 
 
 def upsample2x_to_act(x, n, H, W, C, out):
     _need_cuda(x, out)
-    check(lib().gcd_upsample2x_to_act(_p(x), n, H, W, C, _p(out), _stream()), "upsample2x")
+    with _timed("elem", 0.0, n * H * W * C * (4 + 8)):
+        check(lib().gcd_upsample2x_to_act(_p(x), n, H, W, C, _p(out), _stream()), "upsample2x")
 
 
 def concat_channels(a, b, out, stats=None, n_img=None, groups=32):
@@ -278,7 +282,8 @@ def concat_channels(a, b, out, stats=None, n_img=None, groups=32):
     rows = a.shape[0]
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
     if stats is None:
-        check(lib().gcd_concat_channels(_p(a), a.shape[1], _p(b), b.shape[1], rows, _p(out), _stream()), "concat")
+        with _timed("elem", 0.0, rows * (a.shape[1] + b.shape[1]) * 8):
+            check(lib().gcd_concat_channels(_p(a), a.shape[1], _p(b), b.shape[1], rows, _p(out), _stream()), "concat")
         return
     assert stats.dtype == torch.float64 and rows % n_img == 0 and stats.numel() >= n_img * groups * 2
     C = a.shape[1] + b.shape[1]
@@ -289,37 +294,43 @@ def concat_channels(a, b, out, stats=None, n_img=None, groups=32):
 
 def silu_act(x, out):
     _need_cuda(x, out)
-    check(lib().gcd_silu_act(_p(x), x.numel(), _p(out), _stream()), "silu")
+    with _timed("elem", 0.0, x.numel() * 4):
+        check(lib().gcd_silu_act(_p(x), x.numel(), _p(out), _stream()), "silu")
 
 
 def silu_f32_to_act(x, out):
     _need_cuda(x, out)
     assert x.dtype == torch.float32
-    check(lib().gcd_silu_f32_to_act(_p(x), x.numel(), _p(out), _stream()), "silu_f32")
+    with _timed("elem", 0.0, x.numel() * 6):
+        check(lib().gcd_silu_f32_to_act(_p(x), x.numel(), _p(out), _stream()), "silu_f32")
 
 
 def nchw_to_act_nhwc(x, N, C, HW, Cpad, out):
     _need_cuda(x, out)
     assert x.dtype == torch.float32 and x.is_contiguous()
-    check(lib().gcd_nchw_to_act_nhwc(_p(x), N, C, HW, Cpad, _p(out), _stream()), "nchw_to_act_nhwc")
+    with _timed("elem", 0.0, N * HW * (C * 4 + Cpad * 2)):
+        check(lib().gcd_nchw_to_act_nhwc(_p(x), N, C, HW, Cpad, _p(out), _stream()), "nchw_to_act_nhwc")
 
 
 def nhwc_to_nchw(x, ld, N, C, HW, out):
     _need_cuda(x, out)
     assert x.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
-    check(lib().gcd_nhwc_to_nchw_f32(_p(x), ld, N, C, HW, _p(out), _stream()), "nhwc_to_nchw")
+    with _timed("elem", 0.0, N * HW * C * 8):
+        check(lib().gcd_nhwc_to_nchw_f32(_p(x), ld, N, C, HW, _p(out), _stream()), "nhwc_to_nchw")
 
 
 def vae_time_mix(x, ld, B, T, HW, w, b, out):
     _need_cuda(x, w, b, out)
-    check(lib().gcd_vae_time_mix(_p(x), ld, B, T, HW, _p(w), _p(b), _p(out), _stream()), "vae_time_mix")
+    with _timed("elem", 0.0, B * T * HW * (ld * 4 + 3 * 4)):
+        check(lib().gcd_vae_time_mix(_p(x), ld, B, T, HW, _p(w), _p(b), _p(out), _stream()), "vae_time_mix")
 
 
 def timestep_embedding(t, dim, out_act=None, out_f32=None, max_period=10000.0):
     _need_cuda(t, out_act, out_f32)
     assert t.dtype == torch.float32 and t.is_contiguous()
-    check(lib().gcd_timestep_embedding(_p(t), t.numel(), dim, float(max_period), _p(out_act), _p(out_f32), _stream()),
-          "timestep_embedding")
+    with _timed("elem", 0.0, t.numel() * dim * 2):
+        check(lib().gcd_timestep_embedding(_p(t), t.numel(), dim, float(max_period), _p(out_act), _p(out_f32), _stream()),
+              "timestep_embedding")
 
 
 def spherical_embed(x, w, b, out):
@@ -331,15 +342,17 @@ def spherical_embed(x, w, b, out):
 
 def sampler_prep(x, uc_concat, c_concat, BT, H, W, c_in, out):
     _need_cuda(x, uc_concat, c_concat, out)
-    check(lib().gcd_sampler_prep(_p(x), _p(uc_concat), _p(c_concat), BT, H, W, float(c_in), _p(out), _stream()),
-          "sampler_prep")
+    with _timed("elem", 0.0, BT * H * W * (3 * 16 + 2 * 128)):
+        check(lib().gcd_sampler_prep(_p(x), _p(uc_concat), _p(c_concat), BT, H, W, float(c_in), _p(out), _stream()),
+              "sampler_prep")
 
 
 def sampler_update(x, net_out, ld_net, BT, T, H, W, c_out, c_skip, sigma, dt, scale):
     _need_cuda(x, net_out, scale)
     assert scale.dtype == torch.float32 and scale.numel() == T, "guidance scale must hold one float32 per frame of a clip"
-    check(lib().gcd_sampler_update(_p(x), _p(net_out), ld_net, BT, T, H, W, float(c_out), float(c_skip), float(sigma),
-                                   float(dt), _p(scale), _stream()), "sampler_update")
+    with _timed("elem", 0.0, BT * H * W * (2 * 16 + 2 * ld_net * 4)):
+        check(lib().gcd_sampler_update(_p(x), _p(net_out), ld_net, BT, T, H, W, float(c_out), float(c_skip), float(sigma),
+                                       float(dt), _p(scale), _stream()), "sampler_update")
 
 
 _REPLAYED = 0
