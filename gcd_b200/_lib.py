@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int8, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgcd_b200.so")
+LIB_PATH = os.environ.get("GCD_LIB_PATH") or os.path.join(_HERE, "libgcd_b200.so")   # override: experiments with variant builds
 
 
 class GcdError(RuntimeError):

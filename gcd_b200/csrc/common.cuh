@@ -84,6 +84,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// for waits that are not latency critical (a producer several stages ahead): back off between polls so the spinning
+// thread does not take issue slots from the compute warps of its scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(100);
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {

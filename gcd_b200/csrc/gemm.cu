@@ -600,7 +600,7 @@ static int ilog2(int v) {
 }
 
 constexpr int TC_RETRY_NWG2 = 77;
-template <int BN, int MODE, int NWG>
+template <int BN, int MODE, int NWG, int KC = ((BN <= 160 && MODE == 3) ? 2 : 1)>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mO2,
                      const CUtensorMap& mR1, const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
     static bool configured = false;
@@ -608,7 +608,6 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     constexpr int CL = MODE >= 2 ? 2 : 1;
     // measured in one run (tools/bench_convgemm.py, conv 320->320 @ 28x72x128, pair mode): KC=1 1000, KC=2 1126 TFLOP/s;
     // in mode 2 the doubled stage leaves only 2 stages for BN=160 and is slower.
-    constexpr int KC = (BN <= 160 && MODE == 3) ? 2 : 1;
     constexpr int STAGE_BYTES = KC * (TC_A_BYTES + (MODE == 3 ? BN * 64 : BN * 128));
     if (!configured) {
         GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, KC, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
@@ -738,6 +737,19 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     if (op->N % 256 == 0 || op->N >= 384) BN = 256;
     else if (op->N % 160 == 0) BN = 160;
     else BN = 128;
+    // Small problems (the 9x16 / 18x32 levels: M = 4032 rows -> 16 CTA pairs) are decided by wave quantisation, not by the MMA
+    // width: N = 1280 gives 80 BN=256 pair-tiles on 74 pairs = two waves at 54 % (measured 0.76-0.80 PFLOP/s), 128 BN=160 tiles
+    // = two waves at 86 %. Cost = waves x tile time, tile time ~ BN / measured per-column efficiency of that width.
+    static const int num_sms_h = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    if (BN == 256 && !e.geglu && op->w_batch_stride == 0) {
+        const long m_pairs = ((long)p.ntx * p.nty * p.ntz + 1) / 2, slots = num_sms_h / 2;
+        auto cost = [&](int bn, double eff) {
+            const long tiles = m_pairs * ((op->N + bn - 1) / bn);
+            return (double)((tiles + slots - 1) / slots) * bn / eff;
+        };
+        const double c256 = cost(256, 1.43), c160 = cost(160, 1.20);
+        if (m_pairs * ((op->N + 255) / 256) <= 3 * slots && op->N % 160 == 0 && c160 < 0.9 * c256) BN = 160;
+    }
     static const int bn_env = [] { const char* e = getenv("GCD_TC_BN"); return e ? atoi(e) : 0; }();   // experiments only
     if (bn_env == 128 || bn_env == 160 || bn_env == 256) { if (!e.geglu) BN = bn_env; }
     p.n_tiles = (op->N + BN - 1) / BN;
@@ -812,6 +824,9 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     static const int nwg_env = [] { const char* e = getenv("GCD_TC_NWG"); return e ? atoi(e) : 2; }();
     const int NWG = nwg_env == 3 ? 3 : 2;
     int rc = 0;
+    // (A K = 64-stage variant of the BN = 160 pair tiles for short-K ops with an fp32 residual — room for two residual tiles in
+    // flight per warpgroup, profiles/r1_notes.md §11 — measured SLOWER in situ: K=1280 5.44 -> 7.09 ms per 20 launches,
+    // profiles/r2_notes.md §3; not kept.)
 #define TC_GO(B, M) ((NWG == 3 && (rc = launch_tc<B, M, 3>(mA, mB, mO, mO2, mR1, mR2, p, st)) != TC_RETRY_NWG2) ? rc \
                      : launch_tc<B, M, 2>(mA, mB, mO, mO2, mR1, mR2, p, st))
     switch (BN * 10 + MODE) {

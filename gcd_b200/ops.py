@@ -209,6 +209,13 @@ def zero_stats(stats, n_img, groups=32):
         check(lib().gcd_memset_async(_p(stats), 0, n_img * groups * 2 * 8, _stream()), "memset")
 
 
+def zero_tensor(t):
+    """One memset over a whole (contiguous) workspace tensor."""
+    nbytes = t.numel() * t.element_size()
+    with _timed("elem", 0.0, nbytes):
+        check(lib().gcd_memset_async(_p(t), 0, nbytes, _stream()), "memset")
+
+
 def groupnorm(x, n_img, rows, C, gamma, beta, eps, silu, out, stats, groups=32, have_stats=False):
     """x: [n_img*rows, C] float32 or act -> out act. stats: float64 scratch [n_img*groups*2]; have_stats=True when a
     producing tensor-core op already accumulated them (gcd_epilogue.gn_stats)."""

@@ -77,6 +77,33 @@ class BufferPool:
         return sum(b.numel() * b.element_size() for b in self.bufs.values())
 
 
+class StatsArena:
+    """float64 scratch for the GroupNorm statistics that tensor-core epilogues accumulate (gcd_epilogue.gn_stats): one slot per
+    producer -> consumer hand-off of a forward pass, the WHOLE arena zeroed by one memset at the start of the pass (round 1
+    zeroed a ring buffer before each of the ~130 producers: ~130 extra launches per CFG forward, 2 % of its time in the `elem`
+    class of tools/prof_forward.py)."""
+    SLOTS = 256
+
+    def __init__(self, pool):
+        self.pool, self.slot, self.buf, self.i = pool, 0, None, 0
+
+    def reset(self, n_img):
+        """n_img: the largest number of images (frames) any statistics of this pass are kept for."""
+        need = max(n_img, 64) * 64
+        if need > self.slot:
+            self.slot = need
+            self.buf = self.pool.get("gn_arena", (self.SLOTS * need,), torch.float64)
+        self.i = 0
+        ops.zero_tensor(self.buf)
+
+    def take(self, n_img):
+        need = max(n_img, 64) * 64
+        assert need <= self.slot and self.i < self.SLOTS, "GroupNorm statistics arena exhausted"
+        st = self.buf[self.i * self.slot:(self.i + 1) * self.slot]
+        self.i += 1
+        return st
+
+
 def _geglu_interleave(w, b):
     """Rows [0,H) value / [H,2H) gate (attention.py:93 chunk) -> blocks of 16 value rows followed by 16 gate rows."""
     H = w.shape[0] // 2
@@ -96,6 +123,7 @@ class UNetEngine:
         self.w = {}
         self._pe_cache = {}
         self.debug = None          # set to a list to record every layer's output (tools/bisect_batch.py)
+        self.arena = StatsArena(self.pool)
         self.use_graphs = os.environ.get("GCD_NO_GRAPH", "0") != "1"
         self._graphs = {}
         self._pack(state)
@@ -205,10 +233,8 @@ class UNetEngine:
                       have_stats=stats is not None)
 
     def _stats_req(self, n_img, C, rows_per_img):
-        """Zeroed float64 statistics buffer (ring of 8: producer -> next GroupNorm hand-off) + the epilogue descriptor."""
-        self._ring = (getattr(self, "_ring", 0) + 1) % 8
-        st = self.pool.get(f"gn_ring{self._ring}", (max(n_img, 64) * 64,), torch.float64)
-        ops.zero_stats(st, n_img)
+        """Zeroed float64 statistics slot (StatsArena, zeroed once per forward) + the epilogue descriptor."""
+        st = self.arena.take(n_img)
         return st, (st, C // 32, 32, rows_per_img)
 
     def _mlp_small(self, x_act, k0, k2, out_f32, accumulate):
@@ -403,6 +429,7 @@ class UNetEngine:
         cfg, W, pool, AD = self.cfg, self.w, self.pool, self.AD
         assert n % T == 0
         B = n // T
+        self.arena.reset(n)
         emb_all = self.embed(timesteps, y)
         if ca is None:
             ca = self.cross_attn_vectors(context, T)

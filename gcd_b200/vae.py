@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops, spec
-from .unet import BufferPool, register_param_tree, weights_key
+from .unet import BufferPool, StatsArena, register_param_tree, weights_key
 
 
 class DecoderEngine:
@@ -79,11 +79,17 @@ class DecoderEngine:
                       have_stats=stats is not None)
 
     def _stats_req(self, n_img, C, rows_per_img):
-        """Zeroed statistics buffer for the GroupNorm that consumes the tensor a conv is about to write (fused in its epilogue)."""
-        self._ring = (getattr(self, "_ring", 0) + 1) % 8
-        st = self.pool.get(f"gn_ring{self._ring}", (max(n_img, 64) * 64,), torch.float64)
-        ops.zero_stats(st, n_img)
+        """Zeroed statistics slot for the GroupNorm that consumes the tensor a conv is about to write (fused in its epilogue);
+        the arena is zeroed once per forward."""
+        if getattr(self, "arena", None) is None:
+            self.arena = StatsArena(self.pool)
+        st = self.arena.take(n_img)
         return st, (st, C // 32, 32, rows_per_img)
+
+    def _arena_reset(self, n_img):
+        if getattr(self, "arena", None) is None:
+            self.arena = StatsArena(self.pool)
+        self.arena.reset(n_img)
 
     def _res(self, p, x, cin, cout, n, B, T, H, Wd, tag, x_stats=None):
         """temporal_ae.VideoResBlock.forward (temporal_ae.py:64-83) over ResnetBlock.forward (model.py:127-151).
@@ -150,6 +156,7 @@ class DecoderEngine:
         W, pool, AD = self.w, self.pool, self.AD
         assert n % T == 0
         B = n // T
+        self._arena_reset(n)
         h, hH, hW, hC, hst = None, H, Wd, None, None
         for i, (kind, p, cin, cout) in enumerate(self.plan):
             rows = n * hH * hW
@@ -266,6 +273,7 @@ class EncoderEngine(DecoderEngine):
     def forward_cl(self, x_cl, n, H, Wd, out_nchw):
         """x_cl: act channels-last [n, H, W, 64] (image channels zero-padded); writes float32 NCHW [n, out_ch, H/8, W/8]."""
         W, pool, AD = self.w, self.pool, self.AD
+        self._arena_reset(n)
         h, hH, hW, hst = None, H, Wd, None
         for i, (kind, p, cin, cout) in enumerate(self.plan):
             rows = n * hH * hW
