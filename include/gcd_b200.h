@@ -160,6 +160,13 @@ int gcd_sampler_prep(const float* x, const float* uc_concat, const float* c_conc
 int gcd_sampler_update(float* x, const float* net_out, int ld_net, int BT, int T, int H, int W, float c_out,
                        float c_skip, float sigma, float dt, const float* scale, void* stream);
 
+/* Evaluation-loop image metrics (gcd-model/scripts/test.py:346-496 calculate_metrics; SSIM = scikit-image 0.22.0
+ * structural_similarity(data_range=1, channel_axis=0), masked form = gcd-model/scripts/eval_utils.py:571-664 masked_ssim).
+ * pred, gt: float32 [frames, 3, H, W] in [0, 1]; mask: uint8 [frames, H, W] or NULL. out: float64 [frames, 8], zeroed here:
+ *   {sum (pred-gt)^2, count, same over mask, count, sum SSIM map (3-pixel border cropped), count, same over the 3x eroded mask, count},
+ * sums over the 3 channels. PSNR = 10 log10(count / sum) for data_range 1; SSIM = sum / count. */
+int gcd_frame_metrics(const float* pred, const float* gt, const uint8_t* mask, int frames, int H, int W, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
