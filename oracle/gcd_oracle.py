@@ -7,7 +7,7 @@ It consumes a state dict with the *reference's own parameter names* (SURVEY.md A
 
 PINNING: the reference ships no tests or golden vectors for this path. This restatement is pinned
 against the reference's own modules imported in the build container (oracle/pin_against_reference.py, which also
-writes the golden fixtures under tests/golden/); tests/test_oracle_cpu.py re-checks the oracle against those committed
+writes the golden fixtures under tests/golden/); tests/test_host_cpu.py re-checks the oracle against those committed
 fixtures everywhere (the reference itself cannot travel to the GPU box).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this file.
