@@ -86,30 +86,23 @@ class ClockSampler:
 _CPU_CACHE = {}
 
 
-def cpu_oracle_sample(unet_cfg, vae_cfg, steps, unet_state=None, vae_state=None, lat_hw=(LAT_H, LAT_W)):
-    """Times the CPU oracle port (restatement of the reference's PyTorch path, oracle/gcd_oracle.py) on THIS workload's own
-    shapes: ONE CFG UNet forward (28 frames at `lat_hw` = 72x128) and ONE VAE decode of the 14 frames at that size, fp32, after a
-    small warm-up call (thread pool / allocator). One clip = `steps` such forwards + one decode; every sampler step runs the
-    identical network on identically shaped inputs, so clip time = steps x t_forward + t_decode ("extrapolated from 1 step":
-    a full 25-step clip is ~1 h of host time). The same routine serves `cpu_baseline` and `--impl reference`, so the two legs
-    agree by construction. Returns (latent_frames_per_s, description, cores, seconds_measured)."""
-    from gcd_b200 import spec, synthetic
+def _cpu_leg_worker(spec_json):
+    """Child process of cpu_oracle_sample (python bench.py --cpu-leg '<json>'): times the CPU oracle and prints one JSON line.
+    Runs in its own process so that a host-memory limit or a timeout on the GPU box cannot take the bench line down with it."""
+    from gcd_b200 import flops, spec, synthetic
     from oracle import gcd_oracle as O
-    key = (tuple(sorted((k, str(v)) for k, v in unet_cfg.items())), tuple(sorted((k, str(v)) for k, v in vae_cfg.items())), steps, lat_hw)
-    if key in _CPU_CACHE:
-        return _CPU_CACHE[key]
+    a = json.loads(spec_json)
+    unet_cfg, vae_cfg, (h, w), (vh, vw) = a["unet_cfg"], a["vae_cfg"], a["lat_hw"], a["vae_hw"]
     # Measured on the pool's 128-vCPU B200 hosts (tools/cpu_threads.py, same UNet sample): 16 threads 1.9 s, 32 threads
     # 2.1 s, 64 threads 3.9 s, 128 threads 121 s (the cgroup quota is far below 128 cores) -> use the fastest setting.
     cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
-    if unet_state is None:
-        unet_state = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
-    if vae_state is None:
-        vae_state = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
+    unet_state = synthetic.seeded_state(spec.unet_param_shapes(unet_cfg), seed=0)
+    vae_state = synthetic.seeded_state(spec.decoder_param_shapes(vae_cfg), seed=0)
     n = 2 * T_FRAMES
 
-    def inputs(h, w):
-        x, c, uc, ioi = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, h, w)
+    def inputs(hh, ww):
+        x, c, uc, ioi = synthetic.seeded_inputs(unet_cfg, 1, T_FRAMES, hh, ww)
         xin = torch.cat((torch.cat([x, x]), torch.cat((uc["concat"], c["concat"]))), 1)
         return xin, torch.cat((uc["crossattn"], c["crossattn"])), torch.cat((uc["vector"], c["vector"])), ioi
 
@@ -118,20 +111,73 @@ def cpu_oracle_sample(unet_cfg, vae_cfg, steps, unet_state=None, vae_state=None,
         xin, ctx, y, ioi = inputs(8, 8)                                        # warm-up, untimed
         O.unet_forward(unet_state, unet_cfg, xin, t, ctx, y, T_FRAMES, ioi)
         O.decode_first_stage(vae_state, vae_cfg, torch.randn(T_FRAMES, 4, 8, 8), T_FRAMES)
-        h, w = lat_hw
         xin, ctx, y, ioi = inputs(h, w)
         t0 = time.perf_counter()
         O.unet_forward(unet_state, unet_cfg, xin, t, ctx, y, T_FRAMES, ioi)
         tu = time.perf_counter() - t0
         del xin
-        z = torch.randn(T_FRAMES, 4, h, w)
+        z = torch.randn(T_FRAMES, 4, vh, vw)
         t0 = time.perf_counter()
         O.decode_first_stage(vae_state, vae_cfg, z, T_FRAMES)
         tv = time.perf_counter() - t0
-    full_s = steps * tu + tv
-    desc = (f"1 CFG UNet forward (28 frames, latent {h}x{w}: {tu:.1f} s) + 1 VAE decode of 14 frames at latent {h}x{w} "
-            f"({tv:.1f} s), fp32, {cores} threads, measured once after a small warm-up call; clip = {steps} x forward + decode "
-            f"(extrapolated from 1 step: the steps are identical network calls)")
+    print(json.dumps({"cpu_leg": True, "tu": tu, "tv": tv, "cores": cores}), flush=True)
+
+
+def _run_cpu_leg(unet_cfg, vae_cfg, lat_hw, vae_hw, timeout):
+    arg = json.dumps({"unet_cfg": unet_cfg, "vae_cfg": vae_cfg, "lat_hw": list(lat_hw), "vae_hw": list(vae_hw)})
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+        env.pop(k, None)                      # torchrun pins OMP_NUM_THREADS=1 for its workers
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-leg", arg], capture_output=True, text=True,
+                           timeout=timeout, env=env)
+        for line in r.stdout.splitlines():
+            if line.startswith("{") and "cpu_leg" in line:
+                return json.loads(line), None
+        return None, f"CPU leg exited {r.returncode}: {r.stderr.strip()[-200:]}"
+    except subprocess.TimeoutExpired:
+        return None, f"CPU leg exceeded {timeout} s"
+
+
+def cpu_oracle_sample(unet_cfg, vae_cfg, steps, lat_hw=(LAT_H, LAT_W)):
+    """Times the CPU oracle port (restatement of the reference's PyTorch path, oracle/gcd_oracle.py) on THIS workload's own
+    shapes: ONE CFG UNet forward (28 frames at `lat_hw` = 72x128) and ONE VAE decode of the 14 frames at that size, fp32, after a
+    small warm-up call (thread pool / allocator). One clip = `steps` such forwards + one decode; every sampler step runs the
+    identical network on identically shaped inputs, so clip time = steps x t_forward + t_decode ("extrapolated from 1 step":
+    a full 25-step clip is ~1 h of host time). The same routine serves `cpu_baseline` and `--impl reference`, so the two legs
+    agree by construction. The measurement runs in a child process with a time limit (GCD_CPU_LEG_TIMEOUT, default 1500 s);
+    if the full-size sample cannot run on this host (memory limit, time), a bounded sample (latent 16x24 / decode 8x8) is timed
+    instead and scaled by the exact algorithmic-FLOP ratios — and labelled as such.
+    Returns (latent_frames_per_s, description, cores, seconds_measured)."""
+    from gcd_b200 import flops
+    key = (tuple(sorted((k, str(v)) for k, v in unet_cfg.items())), tuple(sorted((k, str(v)) for k, v in vae_cfg.items())), steps, lat_hw)
+    if key in _CPU_CACHE:
+        return _CPU_CACHE[key]
+    h, w = lat_hw
+    tmo = int(os.environ.get("GCD_CPU_LEG_TIMEOUT", "1500"))
+    res, err = _run_cpu_leg(unet_cfg, vae_cfg, (h, w), (h, w), tmo)
+    if res is not None:
+        tu, tv, cores = res["tu"], res["tv"], res["cores"]
+        desc = (f"1 CFG UNet forward (28 frames, latent {h}x{w}: {tu:.1f} s) + 1 VAE decode of 14 frames at latent {h}x{w} "
+                f"({tv:.1f} s), fp32, {cores} threads, measured once after a small warm-up call; clip = {steps} x forward + decode "
+                f"(extrapolated from 1 step: the steps are identical network calls)")
+        full_s = steps * tu + tv
+    else:
+        sh, sw = min(h, 16), min(w, 24)
+        res, err2 = _run_cpu_leg(unet_cfg, vae_cfg, (sh, sw), (8, 8), 600)
+        if res is None:
+            out = (None, f"CPU oracle could not be timed on this host ({err}; bounded sample: {err2})", 0, 0.0)
+            _CPU_CACHE[key] = out
+            return out
+        tu, tv, cores = res["tu"], res["tv"], res["cores"]
+        n = 2 * T_FRAMES
+        ru = flops.unet_forward_flops(unet_cfg, n, h, w) / flops.unet_forward_flops(unet_cfg, n, sh, sw)
+        rv = flops.decoder_flops(vae_cfg, T_FRAMES, h, w) / flops.decoder_flops(vae_cfg, T_FRAMES, 8, 8)
+        full_s = steps * tu * ru + tv * rv
+        desc = (f"FULL-SIZE SAMPLE UNAVAILABLE ({err}); bounded sample instead: 1 CFG UNet forward at latent {sh}x{sw} ({tu:.2f} s) "
+                f"+ 1 VAE decode at latent 8x8 ({tv:.2f} s), fp32, {cores} threads, scaled to {steps} steps at {h}x{w} by "
+                f"algorithmic FLOP ratios x{ru:.1f} / x{rv:.1f}")
     _CPU_CACHE[key] = (T_FRAMES / full_s, desc, cores, tu + tv)
     return _CPU_CACHE[key]
 
@@ -145,6 +191,9 @@ def run_reference(args, wl):
     lat = tuple(wl.get("latent", (LAT_H, LAT_W)))
     # measured once (one full-size forward + decode is minutes of host time) and reused for every --warmup/--steps iteration
     v, desc, cores, secs = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], lat_hw=lat)
+    if v is None:
+        print(json.dumps({"impl": "reference", "unavailable": desc}), flush=True)
+        return
     line = {"impl": "reference", "metric": "latent-frames/sec", "value": v, "unit": "latent-frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * T_FRAMES / v, "higher_is_better": True, "scaling": "weak",
@@ -248,10 +297,13 @@ def main():
     ap.add_argument("--workload", default="kubric", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads block (BASELINE configs 3/4, CFG-parallel)")
     ap.add_argument("--profile-run", action="store_true",
                     help="for ncu: exactly --warmup/--steps resident steps, no e2e / instrumented / CPU passes, no JSON claims")
     args = ap.parse_args()
+    if args.cpu_leg is not None:
+        return _cpu_leg_worker(args.cpu_leg)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
@@ -388,7 +440,8 @@ def main():
         if extra:
             line["extra_workloads"] = extra
         if world == 1 and not args.no_cpu_baseline and not args.profile_run:
-            v, desc, cores, _ = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], ust, vst, lat_hw=tuple(wl.get("latent", (LAT_H, LAT_W))))
+            del ust, vst                   # the CPU leg runs in a child process: release the 6 GB of host weights first
+            v, desc, cores, _ = cpu_oracle_sample(unet_cfg, vae_cfg, wl["steps"], lat_hw=tuple(wl.get("latent", (LAT_H, LAT_W))))
             line["cpu_baseline"] = {"value": v, "unit": "latent-frames/s", "cores": cores, "kind": "port", "sample": desc}
         print(json.dumps(line), flush=True)
     if world > 1:
