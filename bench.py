@@ -146,7 +146,7 @@ def cpu_oracle_sample(unet_cfg, vae_cfg, steps, lat_hw=(LAT_H, LAT_W)):
     small warm-up call (thread pool / allocator). One clip = `steps` such forwards + one decode; every sampler step runs the
     identical network on identically shaped inputs, so clip time = steps x t_forward + t_decode ("extrapolated from 1 step":
     a full 25-step clip is ~1 h of host time). The same routine serves `cpu_baseline` and `--impl reference`, so the two legs
-    agree by construction. The measurement runs in a child process with a time limit (GCD_CPU_LEG_TIMEOUT, default 1500 s);
+    agree by construction. The measurement runs in a child process with a time limit (GCD_CPU_LEG_TIMEOUT, default 900 s; the full-size sample takes ~5 min on the pool's hosts);
     if the full-size sample cannot run on this host (memory limit, time), a bounded sample (latent 16x24 / decode 8x8) is timed
     instead and scaled by the exact algorithmic-FLOP ratios — and labelled as such.
     Returns (latent_frames_per_s, description, cores, seconds_measured)."""
@@ -155,7 +155,7 @@ def cpu_oracle_sample(unet_cfg, vae_cfg, steps, lat_hw=(LAT_H, LAT_W)):
     if key in _CPU_CACHE:
         return _CPU_CACHE[key]
     h, w = lat_hw
-    tmo = int(os.environ.get("GCD_CPU_LEG_TIMEOUT", "1500"))
+    tmo = int(os.environ.get("GCD_CPU_LEG_TIMEOUT", "900"))
     res, err = _run_cpu_leg(unet_cfg, vae_cfg, (h, w), (h, w), tmo)
     if res is not None:
         tu, tv, cores = res["tu"], res["tv"], res["cores"]

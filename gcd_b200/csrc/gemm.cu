@@ -756,7 +756,8 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     // MODE 3 (CTA pair, cta_group::2 MMA) unless overridden (GCD_TC_MODE=1|2|3), batched weights, or a single M-tile
     static const int mode_env = [] { const char* e = getenv("GCD_TC_MODE"); return e ? atoi(e) : 3; }();
     // short K loops are epilogue-bound: the looser coupling of mode 2 (multicast only) measured faster there
-    const int auto_mode = (p.ntaps * p.kchunks <= 10) ? 2 : 3;
+    static const int auto_k = [] { const char* e = getenv("GCD_TC_AUTO_K"); return e ? atoi(e) : 10; }();   // experiments
+    const int auto_mode = (p.ntaps * p.kchunks <= auto_k) ? 2 : 3;
     const int MODE = (mode_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? (mode_env >= 3 ? auto_mode : 2) : 1;
     const int CL = MODE >= 2 ? 2 : 1;
 
