@@ -756,7 +756,9 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     // MODE 3 (CTA pair, cta_group::2 MMA) unless overridden (GCD_TC_MODE=1|2|3), batched weights, or a single M-tile
     static const int mode_env = [] { const char* e = getenv("GCD_TC_MODE"); return e ? atoi(e) : 3; }();
     // short K loops are epilogue-bound: the looser coupling of mode 2 (multicast only) measured faster there
-    static const int auto_k = [] { const char* e = getenv("GCD_TC_AUTO_K"); return e ? atoi(e) : 10; }();   // experiments
+    // K = 320 (5 chunks): mode 2 is 23-30 % faster; K = 640 (10 chunks): the pair MMA is 7-8 % faster with the round-2 epilogue
+    // (tools/bench_ops.py, GCD_TC_AUTO_K=4 vs 10, same box: GEGLU K=640 0.347 vs 0.378 ms, N=640 residual 0.115 vs 0.123)
+    static const int auto_k = [] { const char* e = getenv("GCD_TC_AUTO_K"); return e ? atoi(e) : 9; }();
     const int auto_mode = (p.ntaps * p.kchunks <= auto_k) ? 2 : 3;
     const int MODE = (mode_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? (mode_env >= 3 ? auto_mode : 2) : 1;
     const int CL = MODE >= 2 ? 2 : 1;
