@@ -43,6 +43,7 @@ _SIGS = {
     "gcd_act_dtype": (c_int, []),
     "gcd_launch_count": (c_int64, []),
     "gcd_tc_run": (c_int, [POINTER(TcOp), c_void_p]),
+    "gcd_tc_override": (None, [c_int, c_int]),
     "gcd_groupnorm_stats": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "gcd_groupnorm_apply": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_float, c_int, c_void_p, c_void_p]),

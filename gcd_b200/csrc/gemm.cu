@@ -680,6 +680,10 @@ static int make_out_map(CUtensorMap* m, const void* ptr, int f32, int ld, int co
     return gcd_make_tmap(m, ptr, 4, dims, str, box, nullptr, bcols * es, f32);
 }
 
+// Experiments only (tools/autotune_tc.py): force the tile width / cluster mode of the following gcd_tc_run calls (0 = automatic).
+static int g_ovr_bn = 0, g_ovr_mode = 0;
+extern "C" void gcd_tc_override(int bn, int mode) { g_ovr_bn = bn; g_ovr_mode = mode; }
+
 extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GCD_REQUIRE(op && op->A && op->W && op->ep.out, "gcd_tc_run: null pointer");
@@ -752,6 +756,7 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     }
     static const int bn_env = [] { const char* e = getenv("GCD_TC_BN"); return e ? atoi(e) : 0; }();   // experiments only
     if (bn_env == 128 || bn_env == 160 || bn_env == 256) { if (!e.geglu) BN = bn_env; }
+    if ((g_ovr_bn == 128 || g_ovr_bn == 160 || g_ovr_bn == 256) && !e.geglu) BN = g_ovr_bn;
     p.n_tiles = (op->N + BN - 1) / BN;
     // MODE 3 (CTA pair, cta_group::2 MMA) unless overridden (GCD_TC_MODE=1|2|3), batched weights, or a single M-tile
     static const int mode_env = [] { const char* e = getenv("GCD_TC_MODE"); return e ? atoi(e) : 3; }();
@@ -760,7 +765,8 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     // (tools/bench_ops.py, GCD_TC_AUTO_K=4 vs 10, same box: GEGLU K=640 0.347 vs 0.378 ms, N=640 residual 0.115 vs 0.123)
     static const int auto_k = [] { const char* e = getenv("GCD_TC_AUTO_K"); return e ? atoi(e) : 9; }();
     const int auto_mode = (p.ntaps * p.kchunks <= auto_k) ? 2 : 3;
-    const int MODE = (mode_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? (mode_env >= 3 ? auto_mode : 2) : 1;
+    int MODE = (mode_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? (mode_env >= 3 ? auto_mode : 2) : 1;
+    if (MODE >= 2 && (g_ovr_mode == 2 || g_ovr_mode == 3)) MODE = g_ovr_mode;
     const int CL = MODE >= 2 ? 2 : 1;
 
     p.bias = e.bias; p.rowvec = e.rowvec; p.rpv = e.rows_per_vec; p.ldv = e.ld_rowvec;

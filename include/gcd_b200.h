@@ -160,6 +160,10 @@ int gcd_sampler_prep(const float* x, const float* uc_concat, const float* c_conc
 int gcd_sampler_update(float* x, const float* net_out, int ld_net, int BT, int T, int H, int W, float c_out,
                        float c_skip, float sigma, float dt, const float* scale, void* stream);
 
+/* Experiments only (tools/autotune_tc.py): force tile width (128 / 160 / 256) and cluster mode (2 = weight multicast, 3 = CTA-pair
+ * MMA) of the following gcd_tc_run calls; 0 = automatic. Not thread-safe. */
+void gcd_tc_override(int bn, int mode);
+
 /* Evaluation-loop image metrics (gcd-model/scripts/test.py:346-496 calculate_metrics; SSIM = scikit-image 0.22.0
  * structural_similarity(data_range=1, channel_axis=0), masked form = gcd-model/scripts/eval_utils.py:571-664 masked_ssim).
  * pred, gt: float32 [frames, 3, H, W] in [0, 1]; mask: uint8 [frames, H, W] or NULL. out: float64 [frames, 8], zeroed here:
