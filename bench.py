@@ -401,9 +401,13 @@ def main():
     line = None
     if rank == 0:
         pk = measured_peaks()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ops.profile() as prof:
+            g0.record()
             step_resident(collective=False)       # rank 0 only: must not enter a collective
+            g1.record()
         summ = prof.summary()
+        prof_wall_ms = g0.elapsed_time(g1)        # eager, per-launch events: slower than the timed (graph-replay) steps
         tc = summ.get("tc_gemm", dict(ms=1e-9, flops=0.0, launches=0))
         tot_ms = sum(d["ms"] for d in summ.values())
         tc_tflops = tc["flops"] / (tc["ms"] / 1e3) / 1e12
@@ -418,6 +422,11 @@ def main():
                 "achieved": round(tc_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(tc_tflops / pk["tflops"], 4),
                 "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": pk["src"],
                 "kernel_share_of_step": round(tc["ms"] / max(tot_ms, 1e-9), 4),
+                "instrumented_step": {"wall_ms": round(prof_wall_ms, 2), "class_sum_ms": round(tot_ms, 2),
+                                      "gap_ms": round(prof_wall_ms - tot_ms, 2),
+                                      "note": "one extra eager step with CUDA events around every launch (all kernel classes "
+                                              "incl. `elem`); gap = time between kernels + torch glue; the timed steps replay the "
+                                              "UNet forward from a CUDA graph"},
                 "whole_path": {"algorithmic_tflop_per_latent_frame": round(per_frame / 1e12, 1),
                                "achieved": round(path_tflops, 1), "frac": round(path_tflops / pk["tflops"], 4)},
                 "classes": {k: {"ms": round(d["ms"], 2), "launches": d["launches"],
