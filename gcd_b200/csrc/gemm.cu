@@ -166,8 +166,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2,
                const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapR2, const TcParams p) {
     constexpr int CL = MODE >= 2 ? 2 : 1;
-    constexpr bool PAIR = MODE == 3;
-    constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;     // weight rows held per CTA and stage
+    constexpr bool PAIR = MODE >= 3;
+    // MODE 4 (WIDE, N == 2*BN == 320): one mainloop pass feeds BOTH N-halves — every activation tile that lands in shared memory
+    // is used by two MMAs (the two weight halves sit side by side in the stage), i.e. a 256 x 320 tile per CTA pair: 36 KB of
+    // operands per 64-wide K chunk instead of 2 x 26 KB (-31 % L2 -> SM traffic; the N = 320 convs are bound by it and, in the
+    // power-capped step, by the energy it costs: profiles/r2_notes.md §7). The accumulators rotate through three 160-column TMEM
+    // regions: virtual tile v (= 2*pass + half) lives in region v % 3, so pass p+1 needs the region of (pass p, half 0) back —
+    // the epilogue of the second half overlaps the next pass.
+    constexpr bool WIDE = MODE == 4;
+    static_assert(!WIDE || (BN == 160 && KC == 1), "wide mode: two 160-column halves, K = 64 stages");
+    constexpr int B_BYTES = (PAIR ? BN * 64 : BN * 128) * (WIDE ? 2 : 1);     // weight bytes held per CTA and 64-wide K chunk
     extern __shared__ __align__(1024) uint8_t smem[];     // SWIZZLE_128B tiles need 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     const int STAGES = p.stages;
@@ -184,9 +192,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + 8;            // [STAGES]  (STAGES <= 8)
     uint64_t* tfull = bars + 16;           // [2]
-    uint64_t* tempty = bars + 18;          // [2]
-    uint64_t* rfull = bars + 20;           // [NWG warpgroups][2] residual tiles landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + 2 * NWG);
+    uint64_t* tempty = bars + 18;          // [2]  (WIDE: [3], one per TMEM region)
+    uint64_t* rfull = bars + 21;           // [NWG warpgroups][2] residual tiles landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21 + 2 * NWG);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -202,10 +210,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], MODE == 2 ? 2 : 1);   // MODE 2: a multicast stage is free once BOTH CTAs' MMAs drained it
         }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], (PAIR ? 2 : 1) * 128 * NWG);   // PAIR: the leader's MMA waits for both CTAs' epilogues
-        }
+        for (int i = 0; i < 2; i++) mbar_init(&tfull[i], 1);
+        for (int i = 0; i < 3; i++) mbar_init(&tempty[i], (PAIR ? 2 : 1) * 128 * NWG);   // PAIR: the leader's MMA waits for both CTAs' epilogues
         for (int i = 0; i < 2 * NWG; i++) mbar_init(&rfull[i], 1);
         fence_barrier_init();
     }
@@ -220,6 +226,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int m_tiles = p.ntx * p.nty * p.ntz;
     const int total = ((m_tiles + CL - 1) / CL) * p.n_tiles;
     const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
+    // i-th tile of this cluster. WIDE: the mainloop walks M-groups (passes); the epilogue sees virtual tiles (group, half) =
+    // tile index 2*group + half, both halves of a group consecutively on the same cluster.
+    auto tile_at = [&](int i) { return WIDE ? 2 * (tile0 + (i >> 1) * tile_step) + (i & 1) : tile0 + i * tile_step; };
     const int kiters = p.ntaps * p.kchunks;
     const int TW = 1 << p.lTW, TH = 1 << p.lTH;
     const int TN = 128 >> (p.lTW + p.lTH);
@@ -233,8 +242,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // ===================== TMA producer =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = tile0; tile < total; tile += tile_step) {
-                const int nt = tile % p.n_tiles;
+            // WIDE: one pass per M-group (both N-halves); otherwise one pass per tile
+            for (int pi = 0;; pi++) {
+                const int tile = WIDE ? tile_at(2 * pi) : tile_at(pi);
+                if (tile >= total) break;
+                const int nt = WIDE ? 0 : tile % p.n_tiles;
                 const int mt = (tile / p.n_tiles) * CL + crank;
                 const int tx = mt % p.ntx;
                 const int ty = (mt / p.ntx) % p.nty;
@@ -254,7 +266,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const int cx = x0 + p.tdx[tap], cy = y0 + p.tdy[tap], cz = z0 + p.tdz[tap];
                         uint8_t* dA = sA + (stage * KC + c) * TC_A_BYTES;
                         uint8_t* dB = sB + (stage * KC + c) * B_BYTES;
-                        if (PAIR) {        // both CTAs' bytes are reported to the leader's barrier
+                        if (WIDE) {        // my 80 weight rows of each N-half, side by side
+                            tma_load_4d_2sm(&mapA, dA, &full[stage], kc * 64, cx, cy, cz);
+                            tma_load_3d_2sm(&mapB, dB, &full[stage], qq * 64, crank * (BN / 2), wy);
+                            tma_load_3d_2sm(&mapB, dB + B_BYTES / 2, &full[stage], qq * 64, BN + crank * (BN / 2), wy);
+                        } else if (PAIR) { // both CTAs' bytes are reported to the leader's barrier
                             tma_load_4d_2sm(&mapA, dA, &full[stage], kc * 64, cx, cy, cz);
                             tma_load_3d_2sm(&mapB, dB, &full[stage], qq * 64, nt * BN + crank * (ntile_w / 2), wy);
                         } else {
@@ -277,13 +293,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = tile0; tile < total; tile += tile_step, it++) {
+            for (;; it++) {
+                const int tile = WIDE ? tile_at(2 * it) : tile_at(it);
+                if (tile >= total) break;
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty[as], aphase ^ 1);
+                uint32_t tacc = tmem_base + as * 256, tacc1 = 0;
+                if (WIDE) {       // virtual tiles 2*it, 2*it+1 -> regions v % 3, each on its (v / 3)-th use
+                    const int v0 = 2 * it, v1 = 2 * it + 1;
+                    mbar_wait(&tempty[v0 % 3], ((v0 / 3) & 1) ^ 1);
+                    mbar_wait(&tempty[v1 % 3], ((v1 / 3) & 1) ^ 1);
+                    tacc = tmem_base + (v0 % 3) * BN;
+                    tacc1 = tmem_base + (v1 % 3) * BN;
+                } else {
+                    mbar_wait(&tempty[as], aphase ^ 1);
+                }
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + as * 256;
-                const int ntile = min(BN, ((p.N - (tile % p.n_tiles) * BN) + 15) & ~15);
+                const int ntile = WIDE ? BN : min(BN, ((p.N - (tile % p.n_tiles) * BN) + 15) & ~15);
                 const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, (uint32_t)ntile, 0, 0);
                 for (int q0 = 0; q0 < kiters; q0 += KC) {
                     const int nch = min(KC, kiters - q0);
@@ -299,6 +325,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 const uint32_t acc = (q0 + c + k) != 0;
                                 if (PAIR) umma_f16_ss_2cta(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, acc);
                                 else umma_f16_ss(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, acc);
+                                if (WIDE)     // second N-half: same A tile, its weight rows B_BYTES/2 further (>> 4 in the descriptor)
+                                    umma_f16_ss_2cta(tacc1, ad + (uint64_t)(k * 2), bd + (uint64_t)(B_BYTES / 32 + k * 2), idesc, acc);
                             }
                         }
                     }
@@ -334,12 +362,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
         // residual prefetcher (leader only): walks this warpgroup's (tile, span, chunk) sequence one chunk ahead.
         // pf_G = spans of the CTA's earlier tiles mod NWG; span pf_s of pf_tile is mine iff (pf_G + pf_s) % NWG == g.
-        int pf_tile = tile0, pf_G = 0, pf_s = g, pf_cc = 0;
+        int pf_i = 0, pf_tile = tile_at(0), pf_G = 0, pf_s = g, pf_cc = 0;
         auto prefetch_residual = [&]() {
             while (pf_tile < total) {                                  // skip tiles where this warpgroup has no span (left)
                 const int ns = nspans(pf_tile);
                 if (pf_s < ns) break;
-                pf_G = (pf_G + ns) % NWG; pf_tile += tile_step; pf_s = (g + NWG - pf_G) % NWG; pf_cc = 0;
+                pf_G = (pf_G + ns) % NWG; pf_tile = tile_at(++pf_i); pf_s = (g + NWG - pf_G) % NWG; pf_cc = 0;
             }
             if (pf_tile >= total) return;
             const int nt = pf_tile % p.n_tiles, mt = (pf_tile / p.n_tiles) * CL + crank;
@@ -382,9 +410,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             myStat[lane] = 0.f; myStat[lane + 32] = 0.f;
             named_bar_sync(BAR_ALL, 128 * NWG);
         }
-        for (int tile = tile0; tile < total; tile += tile_step, it++) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
+        for (;; it++) {
+            const int tile = tile_at(it);
+            if (tile >= total) break;
+            // WIDE: `it` counts virtual tiles; its pass is it >> 1 (accumulator-full barrier of the pass), its TMEM region it % 3
+            const int as = WIDE ? ((it >> 1) & 1) : (it & 1);
+            const uint32_t aphase = WIDE ? ((it >> 2) & 1) : ((it >> 1) & 1);
+            const int te = WIDE ? it % 3 : as;          // tempty barrier of this accumulator
             const int nt = tile % p.n_tiles;
             const int mt = (tile / p.n_tiles) * CL + crank;
             const int tx = mt % p.ntx;
@@ -434,9 +466,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             // also taken without a span in this tile: arriving on tempty below is only legal once the accumulator's previous
             // phase is over, which tfull of THIS tile implies (the MMA waited for it)
+#ifdef GCD_TC_POLL_ONE_WARP
+            // experiment: one warp per warpgroup polls the accumulator barrier, the other three block in bar.sync
+            if (q == 0) mbar_wait(&tfull[as], aphase);
+            named_bar_sync(bar_id, 128);
+#else
             mbar_wait(&tfull[as], aphase);
+#endif
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (WIDE ? (it % 3) * BN : as * 256);
 #pragma unroll 1
             for (int si = s_first; si < ns; si += NWG, ci++) {
                 const int s0 = si * span;
@@ -578,7 +616,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
             tc_fence_before();
-            if (PAIR) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+            if (PAIR) mbar_arrive_cluster(&tempty[te], 0); else mbar_arrive(&tempty[te]);
         }
         if (p.gn_acc && cur_img >= 0) flush_stats();
         if (leader) bulk_wait_read<0>();
@@ -600,7 +638,7 @@ static int ilog2(int v) {
 }
 
 constexpr int TC_RETRY_NWG2 = 77;
-template <int BN, int MODE, int NWG, int KC = ((BN <= 160 && MODE == 3) ? 2 : 1)>
+template <int BN, int MODE, int NWG, int KC = ((BN <= 160 && MODE == 3) ? 2 : 1)>   // (mode 4: KC = 1)
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO, const CUtensorMap& mO2,
                      const CUtensorMap& mR1, const CUtensorMap& mR2, TcParams& p, cudaStream_t st) {
     static bool configured = false;
@@ -608,7 +646,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     constexpr int CL = MODE >= 2 ? 2 : 1;
     // measured in one run (tools/bench_convgemm.py, conv 320->320 @ 28x72x128, pair mode): KC=1 1000, KC=2 1126 TFLOP/s;
     // in mode 2 the doubled stage leaves only 2 stages for BN=160 and is slower.
-    constexpr int STAGE_BYTES = KC * (TC_A_BYTES + (MODE == 3 ? BN * 64 : BN * 128));
+    constexpr int STAGE_BYTES = KC * (TC_A_BYTES + (MODE == 4 ? BN * 128 : MODE == 3 ? BN * 64 : BN * 128));
     if (!configured) {
         GCD_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, KC, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         int dev = 0;
@@ -680,6 +718,10 @@ static int make_out_map(CUtensorMap* m, const void* ptr, int f32, int ld, int co
     return gcd_make_tmap(m, ptr, 4, dims, str, box, nullptr, bcols * es, f32);
 }
 
+static int nwg_cfg() {
+    static const int v = [] { const char* e = getenv("GCD_TC_NWG"); return (e && atoi(e) == 3) ? 3 : 2; }();
+    return v;
+}
 // Experiments only (tools/autotune_tc.py): force the tile width / cluster mode of the following gcd_tc_run calls (0 = automatic).
 static int g_ovr_bn = 0, g_ovr_mode = 0;
 extern "C" void gcd_tc_override(int bn, int mode) { g_ovr_bn = bn; g_ovr_mode = mode; }
@@ -767,6 +809,12 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     const int auto_mode = (p.ntaps * p.kchunks <= auto_k) ? 2 : 3;
     int MODE = (mode_env >= 2 && !p.w_batched && p.ntx * p.nty * p.ntz >= 2) ? (mode_env >= 3 ? auto_mode : 2) : 1;
     if (MODE >= 2 && (g_ovr_mode == 2 || g_ovr_mode == 3)) MODE = g_ovr_mode;
+    // wide tiles (mode 4): N = 320 exactly, pair mode, two warpgroups, and K >= 3840 — measured in situ (tools/prof_forward.py,
+    // same box, GCD_TC_WIDE=0 / GCD_TC_WIDE_K): K=8640 2.43 -> 1.98 ms, K=5760 3.29 -> 3.09, K=2880 4.46 -> 4.52, K <= 1280 slower
+    // (the half-tile epilogue that cannot overlap the next pass is no longer amortised)
+    static const int wide_env = [] { const char* e = getenv("GCD_TC_WIDE"); return e ? atoi(e) : 1; }();
+    static const int wide_k = [] { const char* e = getenv("GCD_TC_WIDE_K"); return e ? atoi(e) : 60; }();
+    if (MODE == 3 && BN == 160 && op->N == 320 && wide_env && nwg_cfg() == 2 && p.ntaps * p.kchunks >= wide_k) MODE = 4;
     const int CL = MODE >= 2 ? 2 : 1;
 
     p.bias = e.bias; p.rowvec = e.rowvec; p.rpv = e.rows_per_vec; p.ldv = e.ld_rowvec;
@@ -830,8 +878,7 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
     // epilogue warpgroups: 2. Three (GCD_TC_NWG=3, experiments) measured 1-20 % SLOWER on every shape of tools/bench_ops.py
     // (profiles/r2_notes.md §1): the third set of staging tiles costs pipeline stages and the 512-thread launch bound caps the
     // epilogue at 128 registers, which serialises its eight independent polynomial chains.
-    static const int nwg_env = [] { const char* e = getenv("GCD_TC_NWG"); return e ? atoi(e) : 2; }();
-    const int NWG = nwg_env == 3 ? 3 : 2;
+    const int NWG = nwg_cfg();
     int rc = 0;
     // (A K = 64-stage variant of the BN = 160 pair tiles for short-K ops with an fp32 residual — room for two residual tiles in
     // flight per warpgroup, profiles/r1_notes.md §11 — measured SLOWER in situ: K=1280 5.44 -> 7.09 ms per 20 launches,
@@ -840,6 +887,7 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
                      : launch_tc<B, M, 2>(mA, mB, mO, mO2, mR1, mR2, p, st))
     switch (BN * 10 + MODE) {
         case 2563: rc = TC_GO(256, 3); break;
+        case 1604: rc = launch_tc<160, 4, 2>(mA, mB, mO, mO2, mR1, mR2, p, st); break;
         case 1603: rc = TC_GO(160, 3); break;
         case 1283: rc = TC_GO(128, 3); break;
         case 2562: rc = TC_GO(256, 2); break;
