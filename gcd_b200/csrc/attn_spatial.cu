@@ -348,9 +348,11 @@ extern "C" int gcd_attention_spatial(const void* qkv, int frames, int tokens, in
         split = (sp && atoi(sp) == 2) ? 2 : 1;
         emu_env = e ? (atoi(e) == 4 ? 4 : 0) : -1;
     }
-    // measured (tools/bench_attn.py): moving every 4th exponential pair to the FMA pipe gains ~2.5 % on the long-sequence level
-    // (9216 tokens) and loses ~1 % on the short ones
-    const int emu = emu_env >= 0 ? emu_env : (tokens >= 4096 ? 4 : 0);
+    // Moving every 4th exponential pair to the FMA pipe gains ~1-2 % on the 9216-token level in a short burst at 1.9 GHz
+    // (tools/bench_attn.py) but LOSES 1.2 % sustained under the power cap the real step runs at (tools/bench_sustained.py: 742 vs
+    // 751 TFLOP/s, 1687 vs 1755 MHz at the same 991 W — the polynomial costs more energy than the MUFU): off by default.
+    const int emu = emu_env >= 0 ? emu_env : 0;
+    (void)tokens;
     const int C = heads * 64;
     CUtensorMap mKV;
     uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)tokens, (uint64_t)frames};

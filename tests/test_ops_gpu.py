@@ -242,8 +242,8 @@ def _attn_ref(qkv, frames, tokens, heads):
     return torch.cat(outs, 2).permute(0, 2, 1, 3).reshape(frames, tokens, C)
 
 
-# 4096 / 9216 tokens: the instantiation bench.py runs at latent 72x128 level 1 (attn_spatial.cu: every 4th exponential pair on
-# the FMA pipe for tokens >= 4096); 4100: ragged last key block on that path; scale 6: logits ~ +-40, forces lazy rescales
+# 4096 / 9216 tokens: the level-1 shape bench.py runs at latent 72x128; 4100: ragged last key block; scale 6: logits ~ +-100,
+# forces lazy rescales. (GCD_FA_EMU=4 — every 4th exponential pair on the FMA pipe — is an experiment path, off by default.)
 @pytest.mark.parametrize("frames,tokens,heads,scale", [
     (2, 256, 5, 1.5), (3, 144, 20, 1.5), (1, 576, 10, 1.5), (2, 100, 5, 1.5), (1, 2304, 5, 1.5), (2, 4, 5, 1.5),
     (2, 4096, 5, 1.5), (2, 9216, 5, 1.5), (1, 4100, 5, 1.5), (1, 9216, 5, 6.0), (1, 2304, 10, 6.0)])
