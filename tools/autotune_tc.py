@@ -62,7 +62,36 @@ for i, o in enumerate(recorded):
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+SUSTAIN = float(os.environ.get("AUTOTUNE_SECONDS", "0"))     # > 0: time each configuration back to back for this long (power-capped)
+TOP = int(os.environ.get("AUTOTUNE_TOP", "0"))               # > 0: only the TOP ops by (burst time x count) of the UNet
+
+
+def timeit_sustained(o, seconds):
+    import time
+    for _ in range(20):
+        real(ctypes.byref(o), st)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    n = 0
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    started = False
+    while True:
+        el = time.time() - t0
+        if not started and el > seconds * 0.4:       # first 40 %: let the clocks settle under the power cap
+            a.record(); started = True; n = 0
+        if el > seconds:
+            break
+        for _ in range(20):
+            real(ctypes.byref(o), st)
+        n += 20
+        torch.cuda.synchronize()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / max(n, 1)
+
+
 def timeit(o, reps=7):
+    if SUSTAIN > 0:
+        return timeit_sustained(o, SUSTAIN)
     for _ in range(2):
         real(ctypes.byref(o), st)
     ts = []
@@ -76,7 +105,15 @@ def timeit(o, reps=7):
 
 
 rows, tot_auto, tot_best = [], {"unet": 0.0, "vae": 0.0}, {"unet": 0.0, "vae": 0.0}
-for key, (o, cnt) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
+order = sorted(groups.items(), key=lambda kv: -kv[1][1])
+if TOP > 0:                           # rank the UNet ops by a quick burst timing x count
+    sus, SUSTAIN = SUSTAIN, 0.0
+    L.gcd_tc_override(0, 0)
+    ranked = sorted(((timeit(o, 3) * cnt, key) for key, (o, cnt) in groups.items() if key[0] == "unet" and not key[-1]), reverse=True)
+    keep = {k for _, k in ranked[:TOP]}
+    order = [(k, v) for k, v in order if k in keep]
+    SUSTAIN = sus
+for key, (o, cnt) in order:
     if key[-1]:                       # batched weights: single-CTA mode only
         continue
     L.gcd_tc_override(0, 0)
