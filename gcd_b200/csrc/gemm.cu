@@ -7,12 +7,15 @@
 //   warp 1   : MMA issuer    — a single thread issues tcgen05.mma (M=128, N=BN, K=16, fp32 accumulate in TMEM),
 //              tcgen05.commit frees smem stages and publishes the accumulator.
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages so the epilogue overlaps the next tile's MMAs).
-//   warps 4-11: epilogue     — two warpgroups alternating 32-column chunks; per chunk: tcgen05.ld the accumulator row of each thread, fused
-//              bias / per-frame vector / SiLU / GEGLU / residual blend, then a swizzled smem staging tile that one
-//              thread hands to the TMA store engine (cp.async.bulk.tensor ... bulk_group). Residual tiles are
-//              prefetched one chunk ahead by TMA loads into swizzled smem. No per-thread global loads/stores of
-//              activations, no bounds checks (TMA clips), compact code (the previous register-transposed epilogue was
-//              instruction-cache bound: profiles/r1_epilogue_icache.md).
+//   warps 4.. : epilogue     — NWG warpgroups (2 by default); the 128-byte-row column spans of the CTA's tile stream are dealt
+//              round-robin to them; per 32-column chunk: tcgen05.ld the accumulator row of each thread, fused bias (+ per-frame
+//              vector) / SiLU / GEGLU / residual blend on packed fp32 pairs, then a swizzled smem staging tile that one thread
+//              hands to the TMA store engine (cp.async.bulk.tensor ... bulk_group). Residual tiles are prefetched one chunk
+//              ahead by TMA loads into swizzled smem. No per-thread global loads/stores of activations, no bounds checks
+//              (TMA clips), compact code (the first register-transposed epilogue was instruction-cache bound:
+//              profiles/r1_notes.md §1).
+// Cluster modes (template MODE): 1 single CTA; 2 weight tile TMA-multicast across a CTA pair; 3 CTA-pair MMA
+// (tcgen05.mma.cta_group::2, M = 256); 4 = 3 with both 160-column halves of an N = 320 row block fed from one activation tile.
 // Replaces cuDNN/cuBLAS calls behind nn.Conv2d / nn.Conv3d / nn.Linear in
 //   gcd-model/sgm/modules/diffusionmodules/openaimodel.py:213-357 (ResBlock), :110-210 (Up/Downsample),
 //   gcd-model/sgm/modules/attention.py:87-113,255-344 (FeedForward/GEGLU, CrossAttention projections),
@@ -113,7 +116,6 @@ struct TcParams {
 };
 
 constexpr int TC_A_BYTES = 128 * 128;
-constexpr int TC_STG_BYTES = 128 * 128;       // one staging tile: 128 rows x <=128 B
 constexpr int TC_SMEM_MAX = 232448;           // 227 KB opt-in maximum per CTA
 
 __device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
