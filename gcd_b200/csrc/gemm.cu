@@ -27,6 +27,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 using namespace ptx;
 
@@ -720,6 +722,33 @@ static int make_out_map(CUtensorMap* m, const void* ptr, int f32, int ld, int co
     return gcd_make_tmap(m, ptr, 4, dims, str, box, nullptr, bcols * es, f32);
 }
 
+// ---- tensor-map cache (host)
+struct TmapKey { gcd_tc_op op; int bn, cl; };
+struct TmapSet { CUtensorMap m[6]; };
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+        uint64_t h = 1469598103934665603ull;                                  // FNV-1a over the (zero-initialised) key bytes
+        for (size_t i = 0; i < sizeof(TmapKey); i++) { h ^= b[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+struct TmapKeyEq { bool operator()(const TmapKey& a, const TmapKey& b) const { return memcmp(&a, &b, sizeof(TmapKey)) == 0; } };
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, TmapSet, TmapKeyHash, TmapKeyEq> g_tmap_cache;
+static bool tmap_cache_find(const TmapKey& k, TmapSet* out) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(k);
+    if (it == g_tmap_cache.end()) return false;
+    *out = it->second;
+    return true;
+}
+static void tmap_cache_put(const TmapKey& k, const TmapSet& v) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();                    // bounded: a new shape set simply refills it
+    g_tmap_cache.emplace(k, v);
+}
+
 static int nwg_cfg() {
     static const int v = [] { const char* e = getenv("GCD_TC_NWG"); return (e && atoi(e) == 3) ? 3 : 2; }();
     return v;
@@ -833,8 +862,20 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
         else stats_skipped = 1;
     }
 
-    // ---- tensor maps
+    // ---- tensor maps: six cuTensorMapEncodeTiled calls per op, cached per (descriptor, tile width, cluster size) — every forward
+    // of the eager paths (VAE decode, generic sampler path, the capture pass of the CUDA graph) re-issues the same few hundred ops
+    // on the same pool buffers. The key is the whole gcd_tc_op (pointers, extents, strides, epilogue tensors) + BN + CL.
     CUtensorMap mA, mB, mO, mO2, mR1, mR2;
+    TmapKey tkey;
+    memset(&tkey, 0, sizeof(tkey));
+    tkey.op = *op; tkey.bn = BN; tkey.cl = CL;
+    tkey.op.ep.a_acc = tkey.op.ep.a_res1 = tkey.op.ep.a_res2 = 0.f;           // scalars / non-tensor fields do not shape the maps
+    tkey.op.ep.bias = nullptr; tkey.op.ep.rowvec = nullptr; tkey.op.ep.gn_stats = nullptr;
+    tkey.op.ep.rows_per_vec = tkey.op.ep.ld_rowvec = 0; tkey.op.ep.act = 0; tkey.op.ep.gn_cpg = tkey.op.ep.gn_groups = 0; tkey.op.ep.gn_rows_per_img = 0;
+    TmapSet hit;
+    if (tmap_cache_find(tkey, &hit)) {
+        mA = hit.m[0]; mB = hit.m[1]; mO = hit.m[2]; mO2 = hit.m[3]; mR1 = hit.m[4]; mR2 = hit.m[5];
+    } else {
     {
         uint64_t dims[4] = {(uint64_t)op->C, (uint64_t)op->Xi, (uint64_t)op->Yi, (uint64_t)op->Zi};
         uint64_t str[3] = {(uint64_t)op->sx * 2, (uint64_t)op->sy * 2, (uint64_t)op->sz * 2};
@@ -876,6 +917,10 @@ extern "C" int gcd_tc_run(const gcd_tc_op* op, void* stream) {
             rc = make_out_map(&mR2, e.res2, e.res2_f32, e.ld_res2, op->N, op->Xo, op->Yo, op->Zo, TW, TH, TN, 32, "res2");
             if (rc) return rc;
         }
+    }
+    TmapSet ts;
+    ts.m[0] = mA; ts.m[1] = mB; ts.m[2] = mO; ts.m[3] = mO2; ts.m[4] = mR1; ts.m[5] = mR2;
+    tmap_cache_put(tkey, ts);
     }
     // epilogue warpgroups: 2. Three (GCD_TC_NWG=3, experiments) measured 1-20 % SLOWER on every shape of tools/bench_ops.py
     // (profiles/r2_notes.md §1): the third set of staging tiles costs pipeline stages and the 512-thread launch bound caps the
