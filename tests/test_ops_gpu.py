@@ -100,6 +100,33 @@ def test_conv2d_3x3(ops, n, H, W, C, Co, stride):
     assert relerr(out, ref) < 3e-5
 
 
+@pytest.mark.parametrize("n,H,W,C,res,f32out", [(3, 24, 64, 448, True, True), (2, 9, 40, 640, False, False), (5, 16, 128, 960, True, True)])
+def test_conv2d_3x3_wide_tiles_n320(ops, n, H, W, C, res, f32out):
+    """N = 320 with K = 9*C >= 3840: tc_gemm mode 4 (256 x 320 pair tiles, both 160-column halves fed from one activation tile,
+    three rotating TMEM regions) incl. ragged M (phantom tiles), several passes per cluster, fp32 residual + fused GroupNorm
+    statistics and 16-bit output."""
+    AD = ops.act_dtype()
+    Co = 320
+    x = rnd(n, H, W, C, dtype=AD)
+    w = rnd(Co, C, 3, 3, scale=(9 * C) ** -0.5, dtype=AD)
+    bias = rnd(Co)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    rows = n * H * W
+    r0 = rnd(rows, Co)
+    out = r0.clone() if f32out else torch.empty(rows, Co, device="cuda", dtype=AD)
+    st = torch.zeros(max(n, 64) * 64, device="cuda", dtype=torch.float64)
+    ok = ops.conv2d_3x3(x, wp, ops.make_ep(out, bias=bias, res1=out if res else None, a_res1=0.5 if res else 1.0,
+                                             gn_stats=(st, Co // 32, 32, H * W)))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(rows, Co)
+    if res:
+        ref = ref + 0.5 * r0
+    assert relerr(out, ref) < (3e-5 if f32out else 1e-3)
+    if ok:
+        v = out.double().view(n, H * W, 32, Co // 32)
+        want = torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1).reshape(-1)
+        assert torch.allclose(st[: n * 64], want, rtol=1e-5, atol=1e-2)
+
+
 @pytest.mark.parametrize("B,T,HW,C,Co", [(2, 14, 144, 128, 128), (1, 14, 4, 64, 320), (2, 14, 512, 320, 320), (3, 5, 96, 64, 64)])
 def test_conv_t3(ops, B, T, HW, C, Co):
     AD = ops.act_dtype()

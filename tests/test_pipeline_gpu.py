@@ -104,6 +104,27 @@ def test_decoder_vs_reference(tag):
     assert e < TOL_DECODE
 
 
+def test_decode_first_stage_in_ragged_chunks_vs_oracle():
+    """DiffusionEngine.decode_first_stage decodes `en_and_decode_n_samples_a_time` frames at a time, each chunk with
+    timesteps = its own length (models/diffusion.py:233-251): 14 frames in chunks of 5 -> 5, 5, 4 (ragged last chunk; the temporal
+    convolutions and clip-wide GroupNorms see only their chunk)."""
+    from gcd_b200 import spec, synthetic
+    from gcd_b200.pipeline import GCDHotPath
+    from oracle import gcd_oracle as O
+    pipe = GCDHotPath(spec.UNET_TINY, spec.VAE_TINY, num_steps=2, num_frames=14, device="cuda")
+    vst = synthetic.seeded_state(spec.decoder_param_shapes(spec.VAE_TINY), seed=0)
+    pipe.decoder.load_state_dict(vst, strict=True)
+    pipe.decoder.cuda()
+    z = torch.randn(14, 4, 8, 16, generator=torch.Generator().manual_seed(3))
+    out = pipe.decode_first_stage(z.cuda(), decoding_t=5)
+    with torch.no_grad():
+        ref = torch.cat([O.decode_first_stage(vst, spec.VAE_TINY, z[i:i + 5], min(5, 14 - i)) for i in range(0, 14, 5)], 0)
+    assert out.shape == ref.shape == (14, 3, 64, 128)
+    assert relerr(out, ref) < TOL_DECODE
+    full = pipe.decode_first_stage(z.cuda())                      # one chunk of 14: a different function of z
+    assert relerr(full[:5], ref[:5]) > 1e-3
+
+
 @pytest.mark.parametrize("tag", ["tiny", "full"])
 def test_encoder_vs_reference(tag):
     """VAE Encoder of the conditioning frames vs the reference Encoder's own outputs; the fused
