@@ -244,9 +244,8 @@ def run_extra_workloads(args, wl, pipe, ust, dev, rank, world, lat, timed, gathe
                      "clips": world, "config": note}
 
     # ---- config 4: same network, 50 steps, max scale 2.5
-    p50 = GCDHotPath(pipe.unet_cfg, pipe.vae_cfg, num_steps=50, num_frames=T_FRAMES, max_scale=2.5, device=dev)
-    p50.unet, p50.decoder = pipe.unet, pipe.decoder                     # share the loaded modules (and their packed engines)
-    p50.model.diffusion_model = pipe.unet
+    p50 = GCDHotPath(pipe.unet_cfg, pipe.vae_cfg, num_steps=50, num_frames=T_FRAMES, max_scale=2.5, device=dev,
+                     unet=pipe.unet, decoder=pipe.decoder)              # share the loaded modules (and their packed engines)
     measure("direct50", p50, pipe.unet_cfg, WORKLOADS["direct50"]["name"])
     # ---- single-clip latency over 2 GPUs (before the ParDom network replaces nothing: it uses the Kubric modules)
     if world >= 2:
@@ -278,10 +277,9 @@ def run_extra_workloads(args, wl, pipe, ust, dev, rank, world, lat, timed, gathe
     pcfg = spec.UNET_PARDOM
     shapes = spec.unet_param_shapes(pcfg)
     pst = {k: ust[k] for k in shapes} if ust is not None else synthetic.seeded_state(shapes, seed=0)
-    pp = GCDHotPath(pcfg, pipe.vae_cfg, num_steps=25, num_frames=T_FRAMES, max_scale=1.5, device=dev)
+    pp = GCDHotPath(pcfg, pipe.vae_cfg, num_steps=25, num_frames=T_FRAMES, max_scale=1.5, device=dev, decoder=pipe.decoder)
     pp.unet.load_state_dict(pst, strict=True)
     pp.unet.to(dev)
-    pp.decoder = pipe.decoder
     measure("pardom", pp, pcfg, WORKLOADS["pardom"]["name"])
     del pp
     return out

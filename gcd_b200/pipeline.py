@@ -11,13 +11,15 @@ from .vae import Encoder, VideoDecoder
 
 class GCDHotPath:
     def __init__(self, unet_cfg=None, vae_cfg=None, num_steps=25, num_frames=14, max_scale=1.5, min_scale=1.0,
-                 sigma_max=700.0, scale_factor=0.18215, device="cuda"):
+                 sigma_max=700.0, scale_factor=0.18215, device="cuda", unet=None, decoder=None):
+        """`unet` / `decoder`: already loaded drop-in modules to share (a second sampler configuration over the same weights —
+        e.g. 50 steps at max scale 2.5 next to the 25-step one — reuses their packed engines); built empty otherwise."""
         self.unet_cfg = dict(unet_cfg or spec.UNET_KUBRIC)
         self.vae_cfg = dict(vae_cfg or spec.VAE_DECODER)
         self.device = torch.device(device)
         self.T, self.scale_factor = num_frames, scale_factor
-        self.unet = VideoUNet(**spec.unet_ctor_kwargs(self.unet_cfg))
-        self.decoder = VideoDecoder(**spec.decoder_ctor_kwargs(self.vae_cfg))
+        self.unet = unet if unet is not None else VideoUNet(**spec.unet_ctor_kwargs(self.unet_cfg))
+        self.decoder = decoder if decoder is not None else VideoDecoder(**spec.decoder_ctor_kwargs(self.vae_cfg))
         self.model = sampling.OpenAIWrapper(self.unet)
         self.denoiser = sampling.Denoiser({"target": "gcd_b200.sampling.VScalingWithEDMcNoise"})
         self.sampler = sampling.EulerEDMSampler(
