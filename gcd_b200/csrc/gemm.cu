@@ -662,10 +662,14 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
     const int RT = (p.has_r1 ? (p.r1f32 ? 16384 : 8192) : 0) + (p.has_r2 ? (p.r2f32 ? 16384 : 8192) : 0);
     const int kiters = p.ntaps * p.kchunks;
     // short K loop => the epilogue is the critical path: double-buffer its staging tiles if >= 3 pipeline stages remain
+    // very short K loops (K <= 384) with a residual are bound by the epilogue's HBM round trips, not by operand delivery: two
+    // pipeline stages suffice there and the shared memory goes to double-buffered residual AND output staging tiles
+    static const int minst_env = [] { const char* e = getenv("GCD_TC_MINST"); return e ? atoi(e) : 2; }();
+    const int need = (kiters <= 6 && RT > 0) ? minst_env : 3;
     auto plan = [&](int fixed, int& obufs, int& stages) {
         // short K loop: first keep two residual chunks in flight (HBM latency), then double-buffer the output staging
-        p.rbufs = (RT > 0 && kiters <= 24 && (TC_SMEM_MAX - (NWG * OT + 2 * NWG * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
-        obufs = (kiters <= 24 && (TC_SMEM_MAX - (2 * NWG * OT + NWG * p.rbufs * RT) - fixed - 256) / STAGE_BYTES >= 3) ? 2 : 1;
+        p.rbufs = (RT > 0 && kiters <= 24 && (TC_SMEM_MAX - (NWG * OT + 2 * NWG * RT) - fixed - 256) / STAGE_BYTES >= need) ? 2 : 1;
+        obufs = (kiters <= 24 && (TC_SMEM_MAX - (2 * NWG * OT + NWG * p.rbufs * RT) - fixed - 256) / STAGE_BYTES >= need) ? 2 : 1;
         stages = (TC_SMEM_MAX - (NWG * obufs * OT + NWG * p.rbufs * RT + fixed) - 256) / STAGE_BYTES;
         if (stages > 8) stages = 8;
     };
