@@ -470,13 +470,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             // also taken without a span in this tile: arriving on tempty below is only legal once the accumulator's previous
             // phase is over, which tfull of THIS tile implies (the MMA waited for it)
-#ifdef GCD_TC_POLL_ONE_WARP
-            // experiment: one warp per warpgroup polls the accumulator barrier, the other three block in bar.sync
-            if (q == 0) mbar_wait(&tfull[as], aphase);
-            named_bar_sync(bar_id, 128);
-#else
             mbar_wait(&tfull[as], aphase);
-#endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (WIDE ? (it % 3) * BN : as * 256);
 #pragma unroll 1
