@@ -46,7 +46,7 @@ def build(force=False, bf16=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", OUT] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    subprocess.check_call([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
     return OUT
 
 
