@@ -256,6 +256,13 @@ class UNetEngine:
             self._pe_cache[key] = pe
         return self._pe_cache[key]
 
+    def _pos_embed_frames(self, p, T, C, n):
+        """The [T, C] time position embedding laid out per frame of the batch ([n, C], frame f -> t = f % T): a rowvec operand."""
+        key = (p, T, n)
+        if key not in self._pe_cache:
+            self._pe_cache[key] = self._pos_embed(p, T, C).repeat(n // T, 1).contiguous()
+        return self._pe_cache[key]
+
     def cross_attn_vectors(self, context, T, static=False):
         """len-1 cross attention == to_out(to_v(ctx)) (+bias): per frame for the spatial blocks, per clip
         (context[::T], video_attention.py:249-253) for the temporal blocks. Step-invariant: the fused sampler computes
@@ -358,8 +365,12 @@ class UNetEngine:
         t = p + ".time_stack.0"
         pe = self._pos_embed(p, T, C)
         xm = pool.get(f"svt_xm{C}", (rows, C), torch.float32)
-        ops.layernorm(x, W[t + ".norm_in.g"], W[t + ".norm_in.b"], a, add=pe, add_rows_per=S, add_mod=T, sum_out=xm)
-        self._ff(t, "ff_in", a, rows, C, ops.make_ep(xm, bias=W[t + ".ff_in.2.b"], res1=xm))
+        # x_mix = x + time_pos_embed[t] is never materialised: norm_in adds the embedding on the fly, and the residual of ff_in
+        # (x_mix + ff_in(norm_in(x_mix)), video_attention.py:118-121) is taken from x with the embedding as the per-frame vector of
+        # the GEMM epilogue (folded into its bias slice) — saves the 4 B/element write-back of the sum
+        ops.layernorm(x, W[t + ".norm_in.g"], W[t + ".norm_in.b"], a, add=pe, add_rows_per=S, add_mod=T)
+        self._ff(t, "ff_in", a, rows, C, ops.make_ep(xm, bias=W[t + ".ff_in.2.b"], res1=x, rowvec=self._pos_embed_frames(p, T, C, n),
+                                                     rows_per_vec=S))
         ops.layernorm(xm, W[t + ".norm1.g"], W[t + ".norm1.b"], a)
         ops.linear(a, W[t + ".qkv.w"], ops.make_ep(qkv))
         ops.attention_temporal(qkv, B, T, S, heads, o)
