@@ -57,6 +57,7 @@ _SIGS = {
     "gcd_upsample2x_to_act": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gcd_concat_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "gcd_concat_channels_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "gcd_concat_channels_stats_act": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gcd_silu_act": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gcd_silu_f32_to_act": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gcd_nchw_to_act_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -58,8 +58,13 @@ __global__ void gn_stats_kernel(const void* __restrict__ in, int64_t rows, int C
 // Channel concat of two fp32 tensors fused with the GroupNorm statistics of the result (the UNet's skip concatenations,
 // openaimodel.py `th.cat([h, hs.pop()], dim=1)` followed by the ResBlock's first GroupNorm): same geometry and the same
 // deterministic reduction as gn_stats_kernel; saves the statistics pass over the concatenated tensor.
+// OUT_ACT: the concatenated tensor is written in the 16-bit activation type only — the consumer ResBlock always has
+// cin != cout there (its 1x1 skip conv and its first GroupNorm read 16-bit operands; nothing reads the fp32 concat), which removes
+// the fp32 write of the concat, the fp32 read of the GroupNorm and the separate cast pass: 20 -> 10 bytes per element.
+// The statistics are those of the fp32 inputs, like the tensor-core epilogues' (sums of the values before the 16-bit rounding).
+template <bool OUT_ACT>
 __global__ void concat_stats_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b, int Cb, int64_t rows,
-                                    int cpg, int rows_per_block, float* __restrict__ out, double* __restrict__ stats,
+                                    int cpg, int rows_per_block, void* __restrict__ out_, double* __restrict__ stats,
                                     int groups) {
     extern __shared__ float sm[];                      // [blockDim.y][C/2][2]
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -76,7 +81,8 @@ __global__ void concat_stats_kernel(const float* __restrict__ a, int Ca, const f
     for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
         const int64_t row = (int64_t)img * rows + r;
         const float4 v = *reinterpret_cast<const float4*>(src + row * ld);
-        *reinterpret_cast<float4*>(out + row * C + c) = v;
+        if (OUT_ACT) *reinterpret_cast<uint2*>(reinterpret_cast<act_t*>(out_) + row * C + c) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + row * C + c) = v;
         sa += v.x + v.y; qa += v.x * v.x + v.y * v.y;
         sb += v.z + v.w; qb += v.z * v.z + v.w * v.w;
     }
@@ -193,7 +199,23 @@ extern "C" int gcd_concat_channels_stats(const float* a, int Ca, const float* b,
     if (rc) return rc;
     const size_t smem = (size_t)block.y * (C / 2) * 2 * sizeof(float);
     GCD_REQUIRE(smem <= 48 * 1024 && (int)(block.x * block.y) >= groups, "concat_stats: unsupported geometry (C=%d)", C);
-    concat_stats_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(a, Ca, b, Cb, rows, C / groups, rpb, out, stats, groups);
+    concat_stats_kernel<false><<<grid, block, smem, (cudaStream_t)stream>>>(a, Ca, b, Cb, rows, C / groups, rpb, out, stats, groups);
+    GCD_CUDA_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+extern "C" int gcd_concat_channels_stats_act(const float* a, int Ca, const float* b, int Cb, int64_t n_img, int64_t rows,
+                                             int groups, void* out, double* stats, void* stream) {
+    GCD_REQUIRE(a && b && out && stats && Ca % 4 == 0 && Cb % 4 == 0, "concat_stats_act: channel counts must be multiples of 4");
+    dim3 grid, block;
+    int rpb;
+    const int C = Ca + Cb;
+    int rc = gn_geometry(n_img, rows, C, groups, &grid, &block, &rpb);
+    if (rc) return rc;
+    const size_t smem = (size_t)block.y * (C / 2) * 2 * sizeof(float);
+    GCD_REQUIRE(smem <= 48 * 1024 && (int)(block.x * block.y) >= groups, "concat_stats_act: unsupported geometry (C=%d)", C);
+    concat_stats_kernel<true><<<grid, block, smem, (cudaStream_t)stream>>>(a, Ca, b, Cb, rows, C / groups, rpb, out, stats, groups);
     GCD_CUDA_CHECK(cudaGetLastError());
     g_launches++;
     return 0;

@@ -294,9 +294,15 @@ def concat_channels(a, b, out, stats=None, n_img=None, groups=32):
         return
     assert stats.dtype == torch.float64 and rows % n_img == 0 and stats.numel() >= n_img * groups * 2
     C = a.shape[1] + b.shape[1]
-    with _timed("groupnorm", 0.0, rows * C * 8):
-        check(lib().gcd_concat_channels_stats(_p(a), a.shape[1], _p(b), b.shape[1], n_img, rows // n_img, groups, _p(out),
-                                              _p(stats), _stream()), "concat_stats")
+    if out.dtype == torch.float32:
+        with _timed("groupnorm", 0.0, rows * C * 8):
+            check(lib().gcd_concat_channels_stats(_p(a), a.shape[1], _p(b), b.shape[1], n_img, rows // n_img, groups, _p(out),
+                                                  _p(stats), _stream()), "concat_stats")
+    else:                                             # 16-bit concat only (the consumer reads 16-bit operands)
+        assert out.dtype == act_dtype() and out.is_contiguous()
+        with _timed("groupnorm", 0.0, rows * C * 6):
+            check(lib().gcd_concat_channels_stats_act(_p(a), a.shape[1], _p(b), b.shape[1], n_img, rows // n_img, groups, _p(out),
+                                                      _p(stats), _stream()), "concat_stats_act")
 
 
 def silu_act(x, out):

@@ -125,6 +125,10 @@ int gcd_concat_channels(const float* a, int Ca, const float* b, int Cb, int64_t 
  * stats[n_img, groups, 2] float64 (sum, sum of squares), zeroed by the caller, accumulated in a fixed order per block. */
 int gcd_concat_channels_stats(const float* a, int Ca, const float* b, int Cb, int64_t n_img, int64_t rows, int groups,
                               float* out, double* stats, void* stream);
+/* Same, the concatenated tensor written in the 16-bit activation type only (statistics of the fp32 inputs): for consumers that read
+ * 16-bit operands anyway — the UNet's output ResBlocks (cin != cout: 1x1 skip conv + first GroupNorm), openaimodel.py `th.cat`. */
+int gcd_concat_channels_stats_act(const float* a, int Ca, const float* b, int Cb, int64_t n_img, int64_t rows, int groups,
+                                  void* out, double* stats, void* stream);
 /* act(x) on act tensor: SiLU (emb_layers SiLU, openaimodel.py:262-268) */
 int gcd_silu_act(const void* in, int64_t n, void* out, void* stream);
 /* SiLU on a float32 tensor, written as act (emb_layers' nn.SiLU on `emb`, openaimodel.py:262-268) */

@@ -387,3 +387,8 @@ def test_concat_channels_with_fused_groupnorm_stats(ops, n, rows, Ca, Cb):
     out2 = torch.empty_like(out)
     ops.concat_channels(a, b, out2)                   # plain variant unchanged
     assert torch.equal(out2, ref)
+    # 16-bit-only concat (what the UNet's output ResBlocks consume): the rounded values, statistics of the fp32 inputs
+    out16 = torch.empty(n * rows, Ca + Cb, device="cuda", dtype=AD)
+    st3 = torch.zeros_like(st)
+    ops.concat_channels(a, b, out16, stats=st3, n_img=n)
+    assert torch.equal(out16, ref.to(AD)) and torch.equal(st3, st)
